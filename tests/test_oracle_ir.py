@@ -1,0 +1,115 @@
+"""The IR oracle has no reference-side golden vectors ("parity unpinned", see oracle/__init__.py);
+these tests check the restatement against values worked out by hand from the published
+sentence-transformers 2.2.2 definitions."""
+import math
+import os
+
+import numpy as np
+import torch
+
+from oracle import ir_oracle as io
+
+
+def _unit(deg, scale=1.0):
+    r = math.radians(deg)
+    return [scale * math.cos(r), scale * math.sin(r)]
+
+
+def _tiny_case():
+    # corpus angles 0,10,30,90,180,45 degrees with different norms (cos_sim must ignore them)
+    corpus_emb = torch.tensor([_unit(0, 2.0), _unit(10, 0.5), _unit(30, 3.0), _unit(90, 1.0),
+                               _unit(180, 0.1), _unit(45, 7.0)], dtype=torch.float32)
+    query_emb = torch.tensor([_unit(2, 1.5), _unit(85, 0.2), _unit(300, 1.0), _unit(170, 4.0)],
+                             dtype=torch.float32)
+    table = torch.cat([query_emb, corpus_emb])
+    queries = {f"q{i}": str(i) for i in range(4)}
+    corpus = {f"d{i}": str(4 + i) for i in range(6)}
+    relevant = {"q0": {"d1", "d5"}, "q1": {"d3"}, "q2": set(), "q3": {"d0", "d2", "d4"}}
+    return io.PrecomputedEmbeddingModel(table), queries, corpus, relevant
+
+
+def test_hand_computed_metrics_cos_sim():
+    model, queries, corpus, relevant = _tiny_case()
+    ev = io.InformationRetrievalEvaluatorOracle(
+        queries, corpus, relevant, corpus_chunk_size=4, mrr_at_k=[10], ndcg_at_k=[10],
+        accuracy_at_k=[1, 3], precision_recall_at_k=[3], map_at_k=[100],
+        score_functions={"cos_sim": io.cos_sim}, write_csv=False)
+    assert ev.queries_ids == ["q0", "q1", "q3"]          # q2 has no relevant docs -> dropped
+    hits = ev.collect_hits(model)
+    assert io.ranked_ids(hits["cos_sim"], 6) == [
+        ["d0", "d1", "d2", "d5", "d3", "d4"],
+        ["d3", "d5", "d2", "d1", "d0", "d4"],
+        ["d4", "d3", "d5", "d2", "d1", "d0"]]
+    m = ev.compute_metrics(hits["cos_sim"])
+    l2 = math.log2
+    ndcg = [(1 / l2(3) + 1 / l2(5)) / (1 / l2(2) + 1 / l2(3)),
+            1.0,
+            (1 / l2(2) + 1 / l2(5) + 1 / l2(7)) / (1 / l2(2) + 1 / l2(3) + 1 / l2(4))]
+    assert m["accuracy@k"] == {1: 2 / 3, 3: 1.0}
+    assert m["precision@k"][3] == np.mean([1 / 3, 1 / 3, 1 / 3])
+    assert m["recall@k"][3] == np.mean([1 / 2, 1.0, 1 / 3])
+    assert m["mrr@k"][10] == (0.5 + 1.0 + 1.0) / 3
+    assert abs(m["ndcg@k"][10] - np.mean(ndcg)) < 1e-15
+    assert m["map@k"][100] == np.mean([(1 / 2 + 2 / 4) / 2, 1.0, (1 / 1 + 2 / 4 + 3 / 6) / 3])
+    # __call__ returns map@max(map_at_k) of the best score function
+    assert ev(model) == m["map@k"][100]
+
+
+def test_chunked_topk_keeps_global_topk():
+    model, queries, corpus, relevant = _tiny_case()
+    ev = io.InformationRetrievalEvaluatorOracle(
+        queries, corpus, relevant, corpus_chunk_size=4, mrr_at_k=[2], ndcg_at_k=[2],
+        accuracy_at_k=[1, 2], precision_recall_at_k=[2], map_at_k=[2],
+        score_functions={"cos_sim": io.cos_sim}, write_csv=False)
+    hits = ev.collect_hits(model)
+    # two chunks (4 + 2 docs), top-2 of each kept -> 4 hits per query, global top-2 survives
+    assert all(len(h) == 4 for h in hits["cos_sim"])
+    assert io.ranked_ids(hits["cos_sim"], 2) == [["d0", "d1"], ["d3", "d5"], ["d4", "d3"]]
+
+
+def test_dot_and_euclid_differ_from_cos():
+    model, queries, corpus, relevant = _tiny_case()
+    q = model.table[:4]
+    c = model.table[4:]
+    torch.testing.assert_close(io.dot_score(q, c), q @ c.T)
+    torch.testing.assert_close(io.euclidean_score(q, c), 1 / (1 + torch.cdist(q, c)))
+    cs = io.cos_sim(q, c)
+    torch.testing.assert_close(cs, (q / q.norm(dim=1, keepdim=True)) @ (c / c.norm(dim=1, keepdim=True)).T)
+    # 1-D inputs are promoted to [1, D]
+    assert io.cos_sim(q[0], c).shape == (1, 6)
+    # zero vector: eps=1e-12 clamp, no NaN
+    z = torch.zeros(1, 2)
+    assert torch.isfinite(io.cos_sim(z, c)).all()
+
+
+def test_topk_dense_equals_list_path():
+    g = torch.Generator().manual_seed(14)
+    q = torch.randn(17, 32, generator=g)
+    c = torch.randn(301, 32, generator=g)
+    table = torch.cat([q, c])
+    model = io.PrecomputedEmbeddingModel(table)
+    queries = {str(i): str(i) for i in range(17)}
+    corpus = {str(i): str(17 + i) for i in range(301)}
+    relevant = {str(i): {str((7 * i) % 301)} for i in range(17)}
+    ev = io.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, corpus_chunk_size=100,
+                                                mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1],
+                                                precision_recall_at_k=[1], map_at_k=[20],
+                                                score_functions={"cos_sim": io.cos_sim}, write_csv=False)
+    hits = ev.collect_hits(model)
+    want = io.ranked_ids(hits["cos_sim"], 20)
+    _, idx = io.topk_dense(q, c, 20, "cos_sim", corpus_chunk_size=100)
+    assert [[str(j) for j in row] for row in idx.tolist()] == want
+
+
+def test_csv_layout(tmp_path):
+    model, queries, corpus, relevant = _tiny_case()
+    ev = io.InformationRetrievalEvaluatorOracle(
+        queries, corpus, relevant, mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1],
+        precision_recall_at_k=[1], map_at_k=[100], name="x",
+        score_functions={"dot_score": io.dot_score, "cos_sim": io.cos_sim})
+    ev(model, output_path=str(tmp_path), epoch=1, steps=2)
+    ev(model, output_path=str(tmp_path), epoch=1, steps=3)
+    lines = open(os.path.join(tmp_path, "Information-Retrieval_evaluation_x_results.csv")).read().splitlines()
+    assert lines[0].split(",")[:4] == ["epoch", "steps", "cos_sim-Accuracy@1", "cos_sim-Precision@1"]
+    assert "dot_score-MAP@100" == lines[0].split(",")[-1]
+    assert len(lines) == 3 and lines[1].startswith("1,2,") and lines[2].startswith("1,3,")
