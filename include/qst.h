@@ -1,0 +1,221 @@
+/*
+ * libqst -- C ABI of the B200 (sm_100a) retrieval-scoring + quadruplet-loss hot path.
+ *
+ * The reference (lucastrefezza/quadruplet-sentence-transformer) is pure Python and has no
+ * FFI of its own; the boundary it exposes for this path is two Python protocols
+ * (SURVEY.md section 8b).  This header is the native boundary underneath the drop-in Python
+ * classes: every entry point cites the reference call it replaces (paths relative to
+ * /root/reference).  INTEGRATION.md shows the reference-side ctypes stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch/C++ types.
+ *   - every function returns 0 on success, <0 on error; qst_last_error() gives the message
+ *     (thread-local).  No exception crosses the boundary.
+ *   - ALL data pointers are DEVICE pointers owned by the caller (inputs, outputs, workspace).
+ *     Workspace sizes come from the matching *_workspace_bytes() call.
+ *   - every launch is asynchronous on the given stream (a cudaStream_t passed as void*).
+ *   - no hidden global state, no hidden allocation, no CPU fallback.
+ */
+#ifndef QST_H_
+#define QST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QST_VERSION 100
+
+typedef void* qst_stream_t; /* cudaStream_t */
+
+enum qst_dtype { QST_F32 = 0, QST_F16 = 1, QST_BF16 = 2 };
+enum qst_reduction { QST_RED_NONE = 0, QST_RED_SUM = 1, QST_RED_MEAN = 2 };
+/* score functions of ir_evauation_script.py:70 */
+enum qst_score { QST_SCORE_COS = 0, QST_SCORE_DOT = 1, QST_SCORE_EUCLID = 2 };
+
+enum qst_status {
+  QST_OK = 0,
+  QST_ERR_INVALID = -1,  /* bad argument (the Python layer raises ValueError before this) */
+  QST_ERR_CUDA = -2,     /* a CUDA runtime/driver call failed */
+  QST_ERR_WORKSPACE = -3,/* workspace too small */
+  QST_ERR_UNSUPPORTED = -4
+};
+
+int qst_version(void);
+const char* qst_last_error(void);
+/* SM count / compute capability of the current device. */
+int qst_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  gamma-quadruplet loss.   Replaces models/losses/losses.py:9-69 (gamma_quadruplet_loss:
+ * three F.triplet_margin_loss calls :35-61 + reductions :64-69) and its autograd backward.
+ *
+ *   d(u,v) = || u - v + eps ||_p          (eps added to the difference, torch pairwise_distance)
+ *   A = max(0, m_pos_neg  + d(a,pos)  - dn(a,pos ,neg ))
+ *   B = max(0, m_part_neg + d(a,part) - dn(a,part,neg ))
+ *   C = max(0, m_pos_part + d(a,pos)  - dn(a,pos ,part))
+ *   dn(a,x,y) = d(a,y), or min(d(a,y), d(x,y)) when swap
+ *   row loss = A + gamma*B + (1-gamma)*C
+ *
+ * Inputs are row-major [B, D] of `dtype`; all arithmetic is fp32; loss outputs are fp32;
+ * gradients are written in `dtype`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qst_quad_params {
+  float gamma;
+  float one_minus_gamma; /* float(1.0 - gamma) evaluated in double, as Python does at losses.py:65 */
+  float margin_pos_neg;
+  float margin_pos_part;
+  float margin_part_neg;
+  float p;    /* > 0; INFINITY allowed */
+  float eps;  /* 1e-6 in the reference (torch default) */
+  int32_t swap;
+} qst_quad_params;
+
+#define QST_QUAD_SAVED_PER_ROW 8 /* 6 distances + 2 pad floats saved by fwd for bwd */
+
+/* Scratch for the cross-row reduction: must be zero-filled ONCE when allocated; the kernels
+ * leave it zeroed again.  Size does not depend on B. */
+size_t qst_quadruplet_workspace_bytes(void);
+
+/* Forward.  loss_out: [B] (QST_RED_NONE) or [1].  saved: [B, QST_QUAD_SAVED_PER_ROW] fp32 or
+ * NULL (no backward wanted, e.g. under torch.no_grad(): models/evaluators.py:82). */
+int qst_quadruplet_fwd(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                       int dtype, int64_t B, int64_t D, const qst_quad_params* prm, int reduction,
+                       float* loss_out, float* saved, void* workspace, qst_stream_t stream);
+
+/* Backward from the distances saved by fwd.  grad_out: fp32 [B] when reduction==NONE else [1]
+ * (device pointer: the upstream gradient of the returned loss).  Any grad pointer may be NULL. */
+int qst_quadruplet_bwd(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                       int dtype, int64_t B, int64_t D, const qst_quad_params* prm, int reduction,
+                       const float* saved, const float* grad_out,
+                       void* g_anchor, void* g_pos, void* g_part, void* g_neg, qst_stream_t stream);
+
+/* One-launch forward+backward for the training step (loss.backward() with upstream 1, scaled by
+ * `upstream`): reads each input once from HBM, writes each gradient once.  8*B*D*sizeof(dtype)
+ * algorithmic bytes. */
+int qst_quadruplet_fwd_bwd(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                           int dtype, int64_t B, int64_t D, const qst_quad_params* prm, int reduction,
+                           float upstream, float* loss_out,
+                           void* g_anchor, void* g_pos, void* g_part, void* g_neg,
+                           void* workspace, qst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  row preparation.  Replaces the F.normalize(p=2, dim=1, eps=1e-12) half of
+ * sentence_transformers.util.cos_sim (called at ir_evauation_script.py:70,
+ * models/evaluators.py:545) and produces the bf16 operand of the tensor-core pass.
+ *
+ *   x: [n, d] of `dtype`, row stride d.
+ *   out_bf16: [n, d_pad] bf16, d_pad = qst_padded_dim(d) (zero padded), rows scaled by
+ *             1/max(||x||,1e-12) when normalize != 0.
+ *   out_inv_norm[n]: 1/max(||x||_2, 1e-12)            (NULL to skip)
+ *   out_sq_norm[n] : ||x||_2^2                        (NULL to skip; euclid score)
+ *   out_err[n]     : || bf16(row) - row_used ||_2     (NULL to skip; rounding residual used by
+ *                    the exactness certificate), row_used = normalised or raw row
+ *   stats (2 floats, device, caller zero-fills before the first call over a corpus):
+ *                    stats[0] = max over rows of out_err, stats[1] = max over rows of ||row_used||
+ *                    (NULL to skip)
+ * ------------------------------------------------------------------------------------------ */
+int64_t qst_padded_dim(int64_t d);
+int qst_prep_rows(const void* x, int dtype, int64_t n, int64_t d, int normalize, void* out_bf16,
+                  float* out_inv_norm, float* out_sq_norm, float* out_err, float* stats,
+                  qst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2+K3  score + top-k.  Replaces, for one corpus shard, the chunk loop of
+ * InformationRetrievalEvaluator.compute_metrices [sentence-transformers 2.2.2]:
+ *   pair_scores = score_function(query_embeddings, sub_corpus_embeddings)      -> K2 (tcgen05)
+ *   torch.topk(pair_scores, min(max_k, chunk), dim=1, largest=True, sorted=False)
+ *   ... sorted(hits, key=score, reverse=True)                                  -> K3
+ * constructed at ir_evauation_script.py:107-123 / models/evaluators.py:572-588.
+ *
+ * K2: bf16 tensor-core scores  S = Qb * Cb^T  tile by tile (TMA -> smem -> tcgen05.mma -> TMEM);
+ *     the epilogue keeps, per query row, only scores above a running threshold (k'-th best seen)
+ *     in a small candidate buffer -- the [Q, N] score matrix never reaches HBM.
+ * K3: per query, selects the k' best candidates, rescoring them exactly in fp32 from the fp32
+ *     masters, sorts descending (ties: lower corpus index first) and emits the top k with a
+ *     certificate:  margin = (k-th exact score) - (k'-th bf16 score) - eps_q, where eps_q is a
+ *     rigorous bound on |bf16 score - exact score|.  margin > 0 proves no document outside the
+ *     candidate set can belong to the exact top k.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qst_topk_plan {
+  int64_t Q, N, D, D_pad;
+  int32_t k, kprime, cap;        /* cap = per-row candidate capacity of one work unit */
+  int32_t m_tiles, n_tiles, stripes, tiles_per_stripe, units;
+  int32_t grid, score;
+  size_t ws_bytes;
+  size_t off_thr, off_cnt, off_cand; /* layout inside the workspace */
+} qst_topk_plan;
+
+/* Fills `plan` for (Q queries, N corpus rows, D dims, top k).  kprime <= 0 picks the default
+ * head-room.  sm_count <= 0 queries the current device. */
+int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kprime, int score, int sm_count,
+                       qst_topk_plan* plan);
+
+/* K2.  q_bf16 [Q, D_pad], c_bf16 [N, D_pad] from qst_prep_rows.  Fills plan->ws. */
+int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16,
+                     void* workspace, qst_stream_t stream);
+
+/* Debug/validation aid: raw tensor-core scores of one call written densely, out[Q, N] fp32.
+ * Same kernel, same tiles, epilogue stores instead of selecting.  Small shapes only. */
+int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad,
+                    float* out, qst_stream_t stream);
+
+/* K3.  Exact fp32 rescoring of the selected candidates and final ordering.
+ *   q_f32 [Q, D], c_f32 [N, D]: fp32 masters; q_inv/c_inv: inverse norms (cos) or NULL (dot).
+ *   q_err [Q] and c_stats (2 floats) from qst_prep_rows feed the certificate; either may be NULL
+ *   (then margin is reported without the eps term).
+ *   idx_offset is added to every emitted corpus index (global id of the shard's row 0).
+ *   out_val [Q, k] fp32 descending, out_idx [Q, k] int64 (-1 / -inf padded when N < k),
+ *   out_margin [Q] fp32 (NULL to skip). */
+int qst_finalize_topk(const qst_topk_plan* plan, const void* workspace,
+                      const float* q_f32, const float* q_inv, const float* q_err,
+                      const float* c_f32, const float* c_inv, const float* c_stats,
+                      int64_t idx_offset, float* out_val, int64_t* out_idx, float* out_margin,
+                      qst_stream_t stream);
+
+/* Exact fp32 brute-force re-scan for the queries whose certificate failed (margin <= 0):
+ * every corpus row is scored in fp32 against each flagged query and rows scoring at least the
+ * current k-th best are collected, which yields the exact top k regardless of bf16 error.
+ * Runs entirely on device (no host read of the flags).  scratch from
+ * qst_exact_rescan_workspace_bytes(). */
+size_t qst_exact_rescan_workspace_bytes(int64_t Q, int k);
+int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score,
+                     const float* q_f32, const float* q_inv, const float* c_f32, const float* c_inv,
+                     int64_t idx_offset, float* out_val, int64_t* out_idx, float* margin_inout,
+                     void* scratch, qst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  merge of per-shard top-k lists (after the NCCL all-gather of SURVEY.md section 8e).
+ *   vals [G, Q, k] fp32 descending per shard, idx [G, Q, k] int64 global ids (-1 = empty).
+ *   out_val/out_idx [Q, k]: global top-k, descending, ties -> lower global id.
+ * ------------------------------------------------------------------------------------------ */
+int qst_merge_topk(const float* vals, const int64_t* idx, int G, int64_t Q, int k,
+                   float* out_val, int64_t* out_idx, qst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  IR metrics.  Replaces InformationRetrievalEvaluator.compute_metrics / compute_dcg_at_k
+ * [sentence-transformers 2.2.2] (Python float64 loops; 5.9 s of 6.7 s at the script's default
+ * k-lists) for rankings that are already on the device.
+ *
+ *   ranked_idx [Q, K] int64 (descending score; -1 = no hit), relevant docs as CSR
+ *   (rel_rowptr [Q+1] int64, rel_cols sorted ascending per row, int64).
+ *   ks [n_ks] int32 cut-offs (a cut-off may exceed K: the list is then simply shorter, as
+ *   top_hits[0:k] is in the reference).  With T = max(K, max ks): log2_tab [T] fp64 =
+ *   np.log2(i+2) computed on the host, so that 1/log2_tab[i] is the same IEEE division the
+ *   reference performs; idcg_tab [T+1] fp64, idcg_tab[j] = sequential sum of the first j terms
+ *   1/log2_tab[i].
+ *   out [6, n_ks, Q] fp64 per-query values in the order
+ *     0 accuracy (0/1)  1 precision  2 recall  3 reciprocal rank  4 ndcg  5 average precision
+ *   The cross-query means are taken on the host with the reference's own reductions
+ *   (numpy.mean / sequential +=) so the final numbers are bit-identical given identical rankings.
+ * ------------------------------------------------------------------------------------------ */
+int qst_ir_metrics(const int64_t* ranked_idx, int64_t Q, int K, const int64_t* rel_rowptr,
+                   const int64_t* rel_cols, const int32_t* ks, int n_ks, const double* log2_tab,
+                   const double* idcg_tab, double* out, qst_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QST_H_ */

@@ -1,0 +1,454 @@
+// K3: candidate selection, exact fp32 rescoring, final ordering and exactness certificate.
+// K6: merge of per-shard top-k lists.   Exact re-scan for uncertified queries.
+//
+// Replaces the tail of sentence-transformers 2.2.2 InformationRetrievalEvaluator:
+//   torch.topk(...)  +  per-query  sorted(hits, key=score, reverse=True)
+// (reference construction sites: /root/reference/ir_evauation_script.py:107-123,
+// models/evaluators.py:572-588).  The fp32 rescoring makes the final order the one the
+// reference's fp32 cos_sim / dot_score produces (up to ties within 1e-6).
+#include "qst_common.cuh"
+
+namespace qst {
+
+constexpr int kFinThreads = 256;
+constexpr int kFinWarps = kFinThreads / 32;
+constexpr int BM_ = 128;  // must match score_select.cu
+
+// ------------------------------------------------------------------------------------------
+// CTA-wide: keep the k largest keys of (keys, idx)[0..n) -> compacted to the front (order
+// arbitrary).  Returns the k-th largest key.  Requires n >= k.  tmp_* hold k entries.
+// ------------------------------------------------------------------------------------------
+__device__ uint32_t block_select_topk(uint32_t* keys, int32_t* idx, int n, int k, uint32_t* tmp_keys,
+                                      int32_t* tmp_idx, int* hist, int* s_misc) {
+  const int tid = threadIdx.x;
+  uint32_t prefix = 0, mask = 0;
+  int krem = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0;  // kFinThreads == 256 bins
+    __syncthreads();
+    for (int i = tid; i < n; i += kFinThreads) {
+      const uint32_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int c[8], ls = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c[i] = hist[tid * 8 + i]; ls += c[i]; }
+      int incl = ls;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (tid + o < 32) incl += t;
+      }
+      const int above = incl - ls;
+      if (above < krem && krem <= above + ls) {
+        int run = above;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+          if (run < krem && krem <= run + c[i]) { s_misc[0] = tid * 8 + i; s_misc[1] = run; }
+          run += c[i];
+        }
+      }
+    }
+    __syncthreads();
+    krem -= s_misc[1];
+    prefix |= (uint32_t)s_misc[0] << shift;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const uint32_t T = prefix;
+  if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
+  __syncthreads();
+  for (int i = tid; i < n; i += kFinThreads) {
+    const uint32_t key = keys[i];
+    bool keep = key > T;
+    if (key == T) keep = atomicAdd(&s_misc[3], 1) < krem;
+    if (keep) {
+      const int p = atomicAdd(&s_misc[2], 1);
+      tmp_keys[p] = key;
+      tmp_idx[p] = idx[i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += kFinThreads) { keys[i] = tmp_keys[i]; idx[i] = tmp_idx[i]; }
+  __syncthreads();
+  return T;
+}
+
+// order: score descending, ties -> lower index first; empty slots (idx < 0) last
+__device__ __forceinline__ bool beats(float sa, int64_t ia, float sb, int64_t ib) {
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// CTA-wide bitonic sort of n2 (power of two) (score, idx) pairs into `beats` order.
+__device__ void block_bitonic_sort(float* sc, int32_t* ix, int n2) {
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < n2 / 2; t += kFinThreads) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;  // first half of each `size` block: best first
+        const bool hi_first = beats(sc[hi], ix[hi], sc[lo], ix[lo]);
+        if (hi_first == up) {
+          const float ts = sc[lo]; sc[lo] = sc[hi]; sc[hi] = ts;
+          const int32_t ti = ix[lo]; ix[lo] = ix[hi]; ix[hi] = ti;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct FinParams {
+  int Q, N, D;
+  int k, kprime, cap, m_tiles, stripes, score;
+  int sm_cap;  // smem candidate capacity (entries)
+  const uint32_t* thr_hint;
+  const int* unit_cnt;
+  const uint2* unit_cand;
+  const float *q_f32, *q_inv, *q_err, *c_f32, *c_inv, *c_stats;
+  int64_t idx_offset;
+  float* out_val;
+  int64_t* out_idx;
+  float* out_margin;
+};
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P) {
+  extern __shared__ uint8_t fsm[];
+  // layout: keys[sm_cap] | idx[sm_cap] | tmp_keys[kprime] | tmp_idx[kprime] | qrow[D] | exact[kprime2]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(fsm);
+  int32_t* idx = reinterpret_cast<int32_t*>(keys + P.sm_cap);
+  uint32_t* tmp_keys = reinterpret_cast<uint32_t*>(idx + P.sm_cap);
+  int32_t* tmp_idx = reinterpret_cast<int32_t*>(tmp_keys + P.kprime);
+  float* qrow = reinterpret_cast<float*>(tmp_idx + P.kprime);
+  __shared__ int hist[256];
+  __shared__ int s_misc[4];
+  __shared__ float s_red[kFinWarps];
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = q / BM_, r = q % BM_;
+
+  // stage the fp32 query row and its squared norm
+  float qq = 0.f;
+  for (int i = tid; i < P.D; i += kFinThreads) {
+    const float v = P.q_f32[(size_t)q * P.D + i];
+    qrow[i] = v;
+    qq = fmaf(v, v, qq);
+  }
+  qq = warp_sum(qq);
+  if (lane == 0) s_red[warp] = qq;
+  __syncthreads();
+  float qnorm2 = 0.f;
+  for (int w = 0; w < kFinWarps; ++w) qnorm2 += s_red[w];
+
+  // 1. gather the candidates of every stripe; compact to the best k' whenever smem fills up
+  bool reduced = false;
+  uint32_t T = 0;
+  int fill = 0;
+  for (int s = 0; s < P.stripes; ++s) {
+    const size_t urow = (size_t)(s * P.m_tiles + m) * BM_ + r;
+    const int cnt = P.unit_cnt[urow];
+    if (fill + cnt > P.sm_cap) {
+      T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
+      fill = P.kprime;
+      reduced = true;
+    }
+    const uint2* src = P.unit_cand + urow * (size_t)P.cap;
+    for (int i = tid; i < cnt; i += kFinThreads) {
+      const uint2 e = src[i];
+      keys[fill + i] = e.x;
+      idx[fill + i] = (int32_t)e.y;
+    }
+    fill += cnt;
+    __syncthreads();
+  }
+  if (fill > P.kprime) {
+    T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
+    fill = P.kprime;
+    reduced = true;
+  } else if (fill == P.kprime && !reduced) {
+    // nothing dropped here, but the epilogue may have dropped scores below the row threshold:
+    // the k'-th key is then the smallest one present
+    uint32_t mn = 0xffffffffu;
+    for (int i = tid; i < fill; i += kFinThreads) mn = min(mn, keys[i]);
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    __shared__ uint32_t s_mn[kFinWarps];
+    if (lane == 0) s_mn[warp] = mn;
+    __syncthreads();
+    mn = s_mn[0];
+    for (int w = 1; w < kFinWarps; ++w) mn = min(mn, s_mn[w]);
+    T = mn;
+    reduced = true;
+  }
+  const int ncand = fill;  // <= kprime
+  const float t_bf = reduced ? key_to_float(T) : -INFINITY;
+
+  // 2. exact fp32 rescoring: one warp per candidate, 128-bit loads of the corpus row
+  float* exact = reinterpret_cast<float*>(keys);  // keys are no longer needed after selection
+  __syncthreads();
+  const float qi = (P.score == QST_SCORE_COS && P.q_inv) ? P.q_inv[q] : 1.0f;
+  const bool vec4 = (P.D % 4) == 0 && ((reinterpret_cast<uintptr_t>(P.c_f32) & 15u) == 0);
+  for (int j = warp; j < ncand; j += kFinWarps) {
+    const int ci = idx[j];
+    const float* crow = P.c_f32 + (size_t)ci * P.D;
+    float acc = 0.f;
+    if (vec4) {
+      const float4* c4 = reinterpret_cast<const float4*>(crow);
+      const float4* q4 = reinterpret_cast<const float4*>(qrow);
+      for (int i = lane; i < P.D / 4; i += 32) {
+        const float4 c = __ldg(c4 + i);
+        const float4 a = q4[i];
+        acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc);
+        acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+      }
+    } else {
+      for (int i = lane; i < P.D; i += 32) acc = fmaf(qrow[i], __ldg(crow + i), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float sc = acc;
+      if (P.score == QST_SCORE_COS) sc = (acc * qi) * (P.c_inv ? P.c_inv[ci] : 1.0f);
+      exact[j] = sc;
+    }
+  }
+  // pad to a power of two for the sort
+  int n2 = 1;
+  while (n2 < ncand) n2 <<= 1;
+  __syncthreads();
+  for (int i = ncand + tid; i < n2; i += kFinThreads) { exact[i] = -INFINITY; idx[i] = -1; }
+  block_bitonic_sort(exact, idx, n2);
+
+  // 3. emit
+  const int kk = P.k;
+  for (int j = tid; j < kk; j += kFinThreads) {
+    const bool ok = j < ncand;
+    P.out_val[(size_t)q * kk + j] = ok ? exact[j] : -INFINITY;
+    P.out_idx[(size_t)q * kk + j] = ok ? (int64_t)idx[j] + P.idx_offset : (int64_t)-1;
+  }
+  if (P.out_margin && tid == 0) {
+    float margin = INFINITY;
+    if (reduced && ncand >= kk) {
+      // rigorous bound on |bf16 tensor-core score - exact score| for this query against any row:
+      //   |dq.c| + |q.dc| + |dq.dc| <= eq*cn + qn*ec + eq*ec      (Cauchy-Schwarz)
+      //   + fp32 accumulation inside the tensor core: <= D * 2^-23 * qn * cn
+      float eps = 0.f;
+      if (P.q_err && P.c_stats) {
+        const float eq = P.q_err[q], ec = P.c_stats[0], cn = P.c_stats[1];
+        const float qn = P.score == QST_SCORE_COS ? (qnorm2 > 0.f ? 1.0f : 0.f) : sqrtf(qnorm2);
+        eps = eq * cn + qn * ec + eq * ec + (float)P.D * 1.2e-7f * qn * cn;
+      }
+      margin = exact[kk - 1] - (t_bf + eps);
+    }
+    P.out_margin[q] = margin;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: merge G descending lists of k entries per query by rank computation (binary searches).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx,
+                                                         int G, int64_t Q, int k, float* __restrict__ out_val,
+                                                         int64_t* __restrict__ out_idx) {
+  const int64_t q = blockIdx.x;
+  const int total = G * k;
+  // default-fill (lists may hold fewer than k valid entries in total)
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    out_val[q * k + j] = -INFINITY;
+    out_idx[q * k + j] = -1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int g = e / k, j = e - g * k;
+    const size_t base = ((size_t)g * Q + q) * k;
+    const float s = vals[base + j];
+    const int64_t id = idx[base + j];
+    if (id < 0) continue;
+    int rank = j;
+    for (int h = 0; h < G; ++h) {
+      if (h == g) continue;
+      const size_t hb = ((size_t)h * Q + q) * k;
+      // number of entries of list h that beat (s, id): lists are sorted in `beats` order
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (beats(vals[hb + mid], idx[hb + mid], s, id)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) { out_val[q * k + rank] = s; out_idx[q * k + rank] = id; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact re-scan of uncertified queries (margin <= 0).  Brute force fp32 on CUDA cores with the
+// already known k-th best exact score as the acceptance threshold, so only a handful of rows
+// per query are appended; the collected rows are then sorted and the top k re-emitted.
+//   step 1  rescan_collect:  grid (corpus blocks, flagged-query batches)
+//   step 2  rescan_emit:     one CTA per query
+// ------------------------------------------------------------------------------------------
+constexpr int kRescanCap = 4096;  // collected rows per flagged query (>= k + ties)
+
+struct RescanScratch {
+  int n_flagged;
+  int pad[3];
+};
+
+__global__ void rescan_list_kernel(const float* margin, int Q, int* flagged, RescanScratch* hdr, int* counts) {
+  // single CTA: ordered list of flagged queries
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int base = 0; base < Q; base += blockDim.x) {
+    const int q = base + threadIdx.x;
+    const bool f = q < Q && !(margin[q] > 0.f);
+    if (f) { const int p = atomicAdd(&s_n, 1); flagged[p] = q; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) hdr->n_flagged = s_n;
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) counts[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k, int score, const float* __restrict__ q_f32,
+                                                             const float* __restrict__ q_inv, const float* __restrict__ c_f32,
+                                                             const float* __restrict__ c_inv, const float* __restrict__ cur_val,
+                                                             const int* __restrict__ flagged, const RescanScratch* hdr,
+                                                             int* counts, float* coll_val, int* coll_idx) {
+  extern __shared__ float s_q[];  // one query row
+  const int nf = hdr->n_flagged;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int f = blockIdx.y; f < nf; f += gridDim.y) {
+    const int q = flagged[f];
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s_q[i] = q_f32[(size_t)q * D + i];
+    __syncthreads();
+    const float thr = cur_val[(size_t)q * k + (k - 1)];  // exact k-th best among the candidates
+    const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
+    for (int row = blockIdx.x * 8 + warp; row < N; row += gridDim.x * 8) {
+      const float* crow = c_f32 + (size_t)row * D;
+      float acc = 0.f;
+      for (int i = lane; i < D; i += 32) acc = fmaf(s_q[i], __ldg(crow + i), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        float sc = acc;
+        if (score == QST_SCORE_COS) sc = (acc * qi) * (c_inv ? c_inv[row] : 1.0f);
+        if (sc >= thr) {
+          const int p = atomicAdd(&counts[q], 1);
+          if (p < kRescanCap) { coll_val[(size_t)f * kRescanCap + p] = sc; coll_idx[(size_t)f * kRescanCap + p] = row; }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kFinThreads) rescan_emit_kernel(int k, int64_t idx_offset, const int* __restrict__ flagged,
+                                                                  const RescanScratch* hdr, const int* __restrict__ counts,
+                                                                  float* coll_val, int* coll_idx, float* out_val,
+                                                                  int64_t* out_idx, float* margin) {
+  __shared__ float sc[kRescanCap];
+  __shared__ int32_t ix[kRescanCap];
+  const int nf = hdr->n_flagged;
+  for (int f = blockIdx.x; f < nf; f += gridDim.x) {
+    const int q = flagged[f];
+    int n = counts[q];
+    if (n > kRescanCap) n = kRescanCap;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n2; i += kFinThreads) {
+      sc[i] = i < n ? coll_val[(size_t)f * kRescanCap + i] : -INFINITY;
+      ix[i] = i < n ? coll_idx[(size_t)f * kRescanCap + i] : -1;
+    }
+    block_bitonic_sort(sc, ix, n2);
+    if (n >= k) {
+      for (int j = threadIdx.x; j < k; j += kFinThreads) {
+        out_val[(size_t)q * k + j] = sc[j];
+        out_idx[(size_t)q * k + j] = (int64_t)ix[j] + idx_offset;
+      }
+      // exact now (unless more than kRescanCap rows tie at the threshold)
+      if (threadIdx.x == 0) margin[q] = counts[q] <= kRescanCap ? INFINITY : 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace qst
+
+using namespace qst;
+
+extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspace, const float* q_f32,
+                                 const float* q_inv, const float* q_err, const float* c_f32, const float* c_inv,
+                                 const float* c_stats, int64_t idx_offset, float* out_val, int64_t* out_idx,
+                                 float* out_margin, qst_stream_t stream) {
+  QST_CHECK_ARG(plan && workspace && q_f32 && c_f32 && out_val && out_idx, "finalize_topk: null argument");
+  QST_CHECK_ARG(plan->score != QST_SCORE_COS || (q_inv && c_inv), "finalize_topk: cos score needs inverse norms");
+  const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
+  FinParams P{};
+  P.Q = (int)plan->Q; P.N = (int)plan->N; P.D = (int)plan->D;
+  P.k = plan->k; P.kprime = plan->kprime; P.cap = plan->cap;
+  P.m_tiles = plan->m_tiles; P.stripes = plan->stripes; P.score = plan->score;
+  int sm_cap = plan->kprime + plan->cap;
+  if (sm_cap < 4096) sm_cap = 4096;
+  P.sm_cap = sm_cap;
+  P.thr_hint = reinterpret_cast<const uint32_t*>(ws + plan->off_thr);
+  P.unit_cnt = reinterpret_cast<const int*>(ws + plan->off_cnt);
+  P.unit_cand = reinterpret_cast<const uint2*>(ws + plan->off_cand);
+  P.q_f32 = q_f32; P.q_inv = q_inv; P.q_err = q_err; P.c_f32 = c_f32; P.c_inv = c_inv; P.c_stats = c_stats;
+  P.idx_offset = idx_offset; P.out_val = out_val; P.out_idx = out_idx; P.out_margin = out_margin;
+  const size_t smem = (size_t)sm_cap * 8 + (size_t)plan->kprime * 8 + round_up((size_t)plan->D * 4, 16);
+  QST_CHECK_ARG(smem <= 200 * 1024, "finalize_topk: D=%lld too large for the rescoring stage", (long long)plan->D);
+  QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<<<(unsigned)plan->Q, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" int qst_merge_topk(const float* vals, const int64_t* idx, int G, int64_t Q, int k, float* out_val,
+                              int64_t* out_idx, qst_stream_t stream) {
+  QST_CHECK_ARG(vals && idx && out_val && out_idx, "merge_topk: null argument");
+  QST_CHECK_ARG(G >= 1 && Q >= 0 && k >= 1, "merge_topk: bad shape G=%d Q=%lld k=%d", G, (long long)Q, k);
+  if (Q == 0) return QST_OK;
+  merge_topk_kernel<<<(unsigned)Q, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(vals, idx, G, Q, k, out_val, out_idx);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" size_t qst_exact_rescan_workspace_bytes(int64_t Q, int k) {
+  (void)k;
+  // header | flagged[Q] | counts[Q] | coll_val[Q*cap] | coll_idx[Q*cap]  (worst case: all flagged)
+  return 256 + round_up((size_t)Q * 4, 256) * 2 + (size_t)Q * kRescanCap * 8;
+}
+
+extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score, const float* q_f32,
+                                const float* q_inv, const float* c_f32, const float* c_inv, int64_t idx_offset,
+                                float* out_val, int64_t* out_idx, float* margin_inout, void* scratch,
+                                qst_stream_t stream) {
+  QST_CHECK_ARG(q_f32 && c_f32 && out_val && out_idx && margin_inout && scratch, "exact_rescan: null argument");
+  QST_CHECK_ARG(score == QST_SCORE_COS || score == QST_SCORE_DOT, "exact_rescan: unsupported score %d", score);
+  QST_CHECK_ARG(D * 4 <= 160 * 1024, "exact_rescan: D too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
+  RescanScratch* hdr = reinterpret_cast<RescanScratch*>(p); p += 256;
+  int* flagged = reinterpret_cast<int*>(p); p += round_up((size_t)Q * 4, 256);
+  int* counts = reinterpret_cast<int*>(p); p += round_up((size_t)Q * 4, 256);
+  float* coll_val = reinterpret_cast<float*>(p); p += (size_t)Q * kRescanCap * 4;
+  int* coll_idx = reinterpret_cast<int*>(p);
+  rescan_list_kernel<<<1, 1024, 0, st>>>(margin_inout, (int)Q, flagged, hdr, counts);
+  QST_LAUNCH_CHECK();
+  const size_t smem = (size_t)D * 4;
+  QST_CUDA(cudaFuncSetAttribute(rescan_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // grid.y strides over the flagged list on the device; its size is only an upper bound on
+  // useful parallelism, so no host read of n_flagged is needed
+  dim3 grid(148, (unsigned)(Q < 32 ? Q : 32));
+  rescan_collect_kernel<<<grid, 256, smem, st>>>((int)N, (int)D, k, score, q_f32, q_inv, c_f32, c_inv, out_val, flagged,
+                                                 hdr, counts, coll_val, coll_idx);
+  QST_LAUNCH_CHECK();
+  rescan_emit_kernel<<<(unsigned)(Q < 1024 ? Q : 1024), kFinThreads, 0, st>>>(k, idx_offset, flagged, hdr, counts, coll_val,
+                                                                              coll_idx, out_val, out_idx, margin_inout);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}

@@ -1,0 +1,412 @@
+// K5: fused gamma-quadruplet loss forward / backward / forward+backward (HBM-bound).
+//
+// Replaces /root/reference/models/losses/losses.py:9-69 (three F.triplet_margin_loss calls and
+// the reductions) and the autograd graph behind them.  One warp owns one row: 128-bit coalesced
+// loads of the four embeddings, up to six p-norm distances accumulated in registers, warp-shuffle
+// reduction, then (fused / backward) the gradient of every input written once.
+//
+// Algorithmic traffic: forward 4*B*D*sizeof(T) read; fused forward+backward 8*B*D*sizeof(T)
+// (4 reads + 4 writes; the second look at the row comes from L1/L2).
+#include "qst_common.cuh"
+
+namespace qst {
+
+enum PMode { PM_2 = 0, PM_1 = 1, PM_INF = 2, PM_GEN = 3 };
+enum Kind { K_FWD = 0, K_BWD = 1, K_FUSED = 2 };
+
+constexpr int kQuadThreads = 128;          // 4 warps = 4 rows in flight per CTA
+constexpr int kQuadMaxBlocks = 148 * 16;   // grid cap (persistent over rows) -> fixed-size workspace
+
+struct QuadWorkspace {
+  unsigned int counter;
+  unsigned int pad;
+  double partial[kQuadMaxBlocks];
+};
+
+template <int PM>
+__device__ __forceinline__ float acc_term(float acc, float e, float p) {
+  if (PM == PM_2) return fmaf(e, e, acc);
+  if (PM == PM_1) return acc + fabsf(e);
+  if (PM == PM_INF) return fmaxf(acc, fabsf(e));
+  return acc + powf(fabsf(e), p);
+}
+template <int PM>
+__device__ __forceinline__ float acc_reduce(float acc) {
+  return PM == PM_INF ? warp_max(acc) : warp_sum(acc);
+}
+template <int PM>
+__device__ __forceinline__ float acc_finish(float acc, float p) {
+  if (PM == PM_2) return sqrtf(acc);
+  if (PM == PM_GEN) return powf(acc, 1.0f / p);
+  return acc;
+}
+
+__device__ __forceinline__ float sgn(float e) { return e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f); }
+
+// d(norm)/d(e) up to the row scalar s (see row_scale): torch norm_backward semantics.
+template <int PM>
+__device__ __forceinline__ float phi(float e, float d, float s, float p) {
+  if (PM == PM_2) return e * s;
+  if (PM == PM_1) return sgn(e) * s;
+  if (PM == PM_INF) return fabsf(e) == d ? sgn(e) * s : 0.f;
+  return e == 0.f ? 0.f : sgn(e) * powf(fabsf(e), p - 1.0f) * s;
+}
+// s: P2 -> 1/d (0 if d==0); P1 -> unused; PINF -> 1/count(|e|==d); PGEN -> d^(1-p) (0 if d==0)
+template <int PM>
+__device__ __forceinline__ float row_scale(float d, float p, float cnt) {
+  if (PM == PM_2) return d > 0.f ? 1.0f / d : 0.f;
+  if (PM == PM_1) return 1.f;
+  if (PM == PM_INF) return cnt > 0.f ? 1.0f / cnt : 0.f;
+  return d > 0.f ? powf(d, 1.0f - p) : 0.f;
+}
+
+// torch.minimum backward: the smaller operand takes the gradient, an exact tie splits it.
+__device__ __forceinline__ void min_sel(float x, float y, float& m, float& sx, float& sy) {
+  m = fminf(x, y);
+  sx = x < y ? 1.f : (x == y ? 0.5f : 0.f);
+  sy = y < x ? 1.f : (x == y ? 0.5f : 0.f);
+}
+
+struct RowTerms {
+  float loss;
+  float w[6];  // d(loss)/d(d_k)
+};
+
+// d0=d(a,pos) d1=d(a,part) d2=d(a,neg) d3=d(pos,neg) d4=d(part,neg) d5=d(pos,part)
+__device__ __forceinline__ RowTerms row_terms(const float d[6], const qst_quad_params& q) {
+  float dnA = d[2], dnB = d[2], dnC = d[1];
+  float sA2 = 1.f, sA3 = 0.f, sB2 = 1.f, sB4 = 0.f, sC1 = 1.f, sC5 = 0.f;
+  if (q.swap) {
+    min_sel(d[2], d[3], dnA, sA2, sA3);
+    min_sel(d[2], d[4], dnB, sB2, sB4);
+    min_sel(d[1], d[5], dnC, sC1, sC5);
+  }
+  const float tA = (q.margin_pos_neg + d[0]) - dnA;
+  const float tB = (q.margin_part_neg + d[1]) - dnB;
+  const float tC = (q.margin_pos_part + d[0]) - dnC;
+  const float A = fmaxf(tA, 0.f), Bv = fmaxf(tB, 0.f), C = fmaxf(tC, 0.f);
+  // clamp_min backward passes the gradient where input >= min
+  const float aA = tA >= 0.f ? 1.f : 0.f;
+  const float aB = tB >= 0.f ? q.gamma : 0.f;
+  const float aC = tC >= 0.f ? q.one_minus_gamma : 0.f;
+  RowTerms r;
+  r.loss = A + q.gamma * Bv + q.one_minus_gamma * C;
+  r.w[0] = aA + aC;
+  r.w[1] = aB - aC * sC1;
+  r.w[2] = -aA * sA2 - aB * sB2;
+  r.w[3] = -aA * sA3;
+  r.w[4] = -aB * sB4;
+  r.w[5] = -aC * sC5;
+  return r;
+}
+
+template <typename T, int VEC>
+struct RowLoader {
+  // loads VEC consecutive elements starting at i (i multiple of VEC when VEC > 1)
+  __device__ __forceinline__ static void load(const T* __restrict__ row, int64_t i, float out[VEC]) {
+    if (VEC == 1) {
+      out[0] = to_f32<T>(row[i]);
+    } else {
+      Vec16<T> v = ld_vec16<T>(row + i);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) out[j] = to_f32<T>(v.v[j]);
+    }
+  }
+  __device__ __forceinline__ static void store(T* __restrict__ row, int64_t i, const float in[VEC]) {
+    if (VEC == 1) {
+      row[i] = from_f32<T>(in[0]);
+    } else {
+      Vec16<T> v;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v.v[j] = from_f32<T>(in[j]);
+      st_vec16<T>(row + i, v);
+    }
+  }
+};
+
+template <typename T, int VEC, int PM>
+__device__ __forceinline__ void row_distances(const T* __restrict__ a, const T* __restrict__ po,
+                                              const T* __restrict__ pa, const T* __restrict__ ne,
+                                              int64_t D, const qst_quad_params& q, int lane, float d[6]) {
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float eps = q.eps, p = q.p;
+  const bool swap = q.swap != 0;
+  for (int64_t i = (int64_t)lane * VEC; i < D; i += 32 * VEC) {
+    float va[VEC], vp[VEC], vq[VEC], vn[VEC];
+    RowLoader<T, VEC>::load(a, i, va);
+    RowLoader<T, VEC>::load(po, i, vp);
+    RowLoader<T, VEC>::load(pa, i, vq);
+    RowLoader<T, VEC>::load(ne, i, vn);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      acc[0] = acc_term<PM>(acc[0], va[j] - vp[j] + eps, p);
+      acc[1] = acc_term<PM>(acc[1], va[j] - vq[j] + eps, p);
+      acc[2] = acc_term<PM>(acc[2], va[j] - vn[j] + eps, p);
+      if (swap) {
+        acc[3] = acc_term<PM>(acc[3], vp[j] - vn[j] + eps, p);
+        acc[4] = acc_term<PM>(acc[4], vq[j] - vn[j] + eps, p);
+        acc[5] = acc_term<PM>(acc[5], vp[j] - vq[j] + eps, p);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d[k] = (k < 3 || swap) ? acc_finish<PM>(acc_reduce<PM>(acc[k]), p) : 0.f;
+}
+
+// w[k] already carries the upstream gradient of the row.
+template <typename T, int VEC, int PM>
+__device__ __forceinline__ void row_gradients(const T* __restrict__ a, const T* __restrict__ po,
+                                              const T* __restrict__ pa, const T* __restrict__ ne,
+                                              int64_t D, const qst_quad_params& q, int lane,
+                                              const float d[6], const float w[6],
+                                              T* __restrict__ ga, T* __restrict__ gp,
+                                              T* __restrict__ gq, T* __restrict__ gn) {
+  const float eps = q.eps, p = q.p;
+  const bool swap = q.swap != 0;
+  float cnt[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+  if (PM == PM_INF) {  // number of maximal elements per distance (ties share the gradient)
+    float c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = (int64_t)lane * VEC; i < D; i += 32 * VEC) {
+      float va[VEC], vp[VEC], vq[VEC], vn[VEC];
+      RowLoader<T, VEC>::load(a, i, va);
+      RowLoader<T, VEC>::load(po, i, vp);
+      RowLoader<T, VEC>::load(pa, i, vq);
+      RowLoader<T, VEC>::load(ne, i, vn);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        c[0] += fabsf(va[j] - vp[j] + eps) == d[0] ? 1.f : 0.f;
+        c[1] += fabsf(va[j] - vq[j] + eps) == d[1] ? 1.f : 0.f;
+        c[2] += fabsf(va[j] - vn[j] + eps) == d[2] ? 1.f : 0.f;
+        if (swap) {
+          c[3] += fabsf(vp[j] - vn[j] + eps) == d[3] ? 1.f : 0.f;
+          c[4] += fabsf(vq[j] - vn[j] + eps) == d[4] ? 1.f : 0.f;
+          c[5] += fabsf(vp[j] - vq[j] + eps) == d[5] ? 1.f : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cnt[k] = warp_sum(c[k]);
+  }
+  float s[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s[k] = row_scale<PM>(d[k], p, cnt[k]) * w[k];
+
+  for (int64_t i = (int64_t)lane * VEC; i < D; i += 32 * VEC) {
+    float va[VEC], vp[VEC], vq[VEC], vn[VEC];
+    RowLoader<T, VEC>::load(a, i, va);
+    RowLoader<T, VEC>::load(po, i, vp);
+    RowLoader<T, VEC>::load(pa, i, vq);
+    RowLoader<T, VEC>::load(ne, i, vn);
+    float oa[VEC], op[VEC], oq[VEC], on[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float f0 = phi<PM>(va[j] - vp[j] + eps, d[0], s[0], p);
+      const float f1 = phi<PM>(va[j] - vq[j] + eps, d[1], s[1], p);
+      const float f2 = phi<PM>(va[j] - vn[j] + eps, d[2], s[2], p);
+      float f3 = 0.f, f4 = 0.f, f5 = 0.f;
+      if (swap) {
+        f3 = phi<PM>(vp[j] - vn[j] + eps, d[3], s[3], p);
+        f4 = phi<PM>(vq[j] - vn[j] + eps, d[4], s[4], p);
+        f5 = phi<PM>(vp[j] - vq[j] + eps, d[5], s[5], p);
+      }
+      oa[j] = f0 + f1 + f2;
+      op[j] = -f0 + f3 + f5;
+      oq[j] = -f1 + f4 - f5;
+      on[j] = -f2 - f3 - f4;
+    }
+    if (ga) RowLoader<T, VEC>::store(ga, i, oa);
+    if (gp) RowLoader<T, VEC>::store(gp, i, op);
+    if (gq) RowLoader<T, VEC>::store(gq, i, oq);
+    if (gn) RowLoader<T, VEC>::store(gn, i, on);
+  }
+}
+
+struct QuadArgs {
+  const void *a, *po, *pa, *ne;
+  void *ga, *gp, *gq, *gn;
+  int64_t B, D;
+  qst_quad_params prm;
+  int reduction;
+  float upstream;         // fused: scalar upstream gradient
+  float* loss_out;        // fwd / fused
+  float* saved;           // fwd: out (may be null); bwd: in
+  const float* grad_out;  // bwd
+  QuadWorkspace* ws;
+};
+
+template <typename T, int VEC, int PM, int KIND>
+__global__ void __launch_bounds__(kQuadThreads) quad_kernel(const QuadArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int kWarps = kQuadThreads / 32;
+  const int64_t D = g.D;
+  const float inv_b = g.reduction == QST_RED_MEAN ? 1.0f / (float)g.B : 1.0f;
+  double block_sum = 0.0;  // meaningful in lane 0 of each warp
+
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < g.B; row += (int64_t)gridDim.x * kWarps) {
+    const T* a = reinterpret_cast<const T*>(g.a) + row * D;
+    const T* po = reinterpret_cast<const T*>(g.po) + row * D;
+    const T* pa = reinterpret_cast<const T*>(g.pa) + row * D;
+    const T* ne = reinterpret_cast<const T*>(g.ne) + row * D;
+    float d[6];
+    if (KIND == K_BWD) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d[k] = g.saved[row * QST_QUAD_SAVED_PER_ROW + k];
+    } else {
+      row_distances<T, VEC, PM>(a, po, pa, ne, D, g.prm, lane, d);
+    }
+    RowTerms t = row_terms(d, g.prm);
+    if (KIND != K_BWD) {
+      if (lane == 0) {
+        if (g.saved) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) g.saved[row * QST_QUAD_SAVED_PER_ROW + k] = d[k];
+        }
+        if (g.reduction == QST_RED_NONE) g.loss_out[row] = t.loss;
+      }
+      block_sum += (double)t.loss;
+    }
+    if (KIND != K_FWD) {
+      float up;
+      if (KIND == K_BWD) up = (g.reduction == QST_RED_NONE ? g.grad_out[row] : g.grad_out[0] * inv_b);
+      else up = g.upstream * inv_b;
+      float w[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w[k] = t.w[k] * up;
+      T* ga = g.ga ? reinterpret_cast<T*>(g.ga) + row * D : nullptr;
+      T* gp = g.gp ? reinterpret_cast<T*>(g.gp) + row * D : nullptr;
+      T* gq = g.gq ? reinterpret_cast<T*>(g.gq) + row * D : nullptr;
+      T* gn = g.gn ? reinterpret_cast<T*>(g.gn) + row * D : nullptr;
+      row_gradients<T, VEC, PM>(a, po, pa, ne, D, g.prm, lane, d, w, ga, gp, gq, gn);
+    }
+  }
+
+  if (KIND != K_BWD && g.reduction != QST_RED_NONE) {
+    // deterministic two-level reduction: warps -> CTA partial -> last CTA sums partials in order
+    __shared__ double s_part[kWarps];
+    __shared__ bool s_last;
+    if (lane == 0) s_part[warp] = block_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += s_part[w];
+      g.ws->partial[blockIdx.x] = tot;
+      __threadfence();
+      const unsigned int ticket = atomicAdd(&g.ws->counter, 1u);
+      s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+      __threadfence();
+      double acc = 0.0;
+      for (int i = lane; i < (int)gridDim.x; i += 32) acc += __ldcg(&g.ws->partial[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        if (g.reduction == QST_RED_MEAN) acc /= (double)g.B;
+        g.loss_out[0] = (float)acc;
+        g.ws->counter = 0u;  // leave the workspace zeroed for the next launch
+      }
+    }
+  }
+}
+
+template <typename T, int VEC, int KIND>
+static void launch_pm(const QuadArgs& a, int pm, int grid, cudaStream_t st) {
+  switch (pm) {
+    case PM_2: quad_kernel<T, VEC, PM_2, KIND><<<grid, kQuadThreads, 0, st>>>(a); break;
+    case PM_1: quad_kernel<T, VEC, PM_1, KIND><<<grid, kQuadThreads, 0, st>>>(a); break;
+    case PM_INF: quad_kernel<T, VEC, PM_INF, KIND><<<grid, kQuadThreads, 0, st>>>(a); break;
+    default: quad_kernel<T, VEC, PM_GEN, KIND><<<grid, kQuadThreads, 0, st>>>(a); break;
+  }
+}
+
+template <typename T, int KIND>
+static void launch_vec(const QuadArgs& a, int pm, bool vec_ok, int grid, cudaStream_t st) {
+  if (vec_ok) launch_pm<T, 16 / sizeof(T), KIND>(a, pm, grid, st);
+  else launch_pm<T, 1, KIND>(a, pm, grid, st);
+}
+
+static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
+  QST_CHECK_ARG(a.B >= 0 && a.D >= 1, "quadruplet: bad shape B=%lld D=%lld", (long long)a.B, (long long)a.D);
+  QST_CHECK_ARG(dtype == QST_F32 || dtype == QST_F16 || dtype == QST_BF16, "quadruplet: bad dtype %d", dtype);
+  QST_CHECK_ARG(a.reduction >= QST_RED_NONE && a.reduction <= QST_RED_MEAN, "quadruplet: bad reduction %d", a.reduction);
+  QST_CHECK_ARG(a.prm.p > 0.f, "p must be positive, %g given", (double)a.prm.p);
+  QST_CHECK_ARG(a.a && a.po && a.pa && a.ne, "quadruplet: null input pointer");
+  if (kind != K_BWD) QST_CHECK_ARG(a.loss_out != nullptr, "quadruplet: null loss_out");
+  if (kind != K_BWD && a.reduction != QST_RED_NONE) QST_CHECK_ARG(a.ws != nullptr, "quadruplet: null workspace");
+  if (kind == K_BWD) QST_CHECK_ARG(a.saved && a.grad_out, "quadruplet bwd: null saved/grad_out");
+  if (a.B == 0) {
+    if (kind != K_BWD && a.reduction != QST_RED_NONE) {
+      // sum over nothing = 0, mean over nothing = nan (torch semantics)
+      const float v = a.reduction == QST_RED_MEAN ? NAN : 0.f;
+      QST_CUDA(cudaMemcpyAsync(a.loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    return QST_OK;
+  }
+  const int pm = a.prm.p == 2.0f ? PM_2 : (a.prm.p == 1.0f ? PM_1 : (isinf(a.prm.p) ? PM_INF : PM_GEN));
+  const size_t esz = dtype == QST_F32 ? 4 : 2;
+  const int vec = (int)(16 / esz);
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  bool vec_ok = (a.D % vec) == 0 && aligned(a.a) && aligned(a.po) && aligned(a.pa) && aligned(a.ne) &&
+                aligned(a.ga) && aligned(a.gp) && aligned(a.gq) && aligned(a.gn);
+  const int warps = kQuadThreads / 32;
+  int grid = (int)(ceil_div(a.B, warps) < kQuadMaxBlocks ? ceil_div(a.B, warps) : kQuadMaxBlocks);
+#define QST_QUAD_LAUNCH(T)                                                   \
+  do {                                                                       \
+    if (kind == K_FWD) launch_vec<T, K_FWD>(a, pm, vec_ok, grid, st);        \
+    else if (kind == K_BWD) launch_vec<T, K_BWD>(a, pm, vec_ok, grid, st);   \
+    else launch_vec<T, K_FUSED>(a, pm, vec_ok, grid, st);                    \
+  } while (0)
+  if (dtype == QST_F32) QST_QUAD_LAUNCH(float);
+  else if (dtype == QST_F16) QST_QUAD_LAUNCH(__half);
+  else QST_QUAD_LAUNCH(__nv_bfloat16);
+#undef QST_QUAD_LAUNCH
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+}  // namespace qst
+
+using namespace qst;
+
+extern "C" size_t qst_quadruplet_workspace_bytes(void) { return sizeof(QuadWorkspace); }
+
+extern "C" int qst_quadruplet_fwd(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                                  int dtype, int64_t B, int64_t D, const qst_quad_params* prm, int reduction,
+                                  float* loss_out, float* saved, void* workspace, qst_stream_t stream) {
+  QST_CHECK_ARG(prm != nullptr, "quadruplet: null params");
+  QuadArgs a{};
+  a.a = x_anchor; a.po = x_pos; a.pa = x_part; a.ne = x_neg;
+  a.B = B; a.D = D; a.prm = *prm; a.reduction = reduction;
+  a.loss_out = loss_out; a.saved = saved; a.ws = reinterpret_cast<QuadWorkspace*>(workspace);
+  return quad_dispatch(K_FWD, a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int qst_quadruplet_bwd(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                                  int dtype, int64_t B, int64_t D, const qst_quad_params* prm, int reduction,
+                                  const float* saved, const float* grad_out,
+                                  void* g_anchor, void* g_pos, void* g_part, void* g_neg, qst_stream_t stream) {
+  QST_CHECK_ARG(prm != nullptr, "quadruplet: null params");
+  QuadArgs a{};
+  a.a = x_anchor; a.po = x_pos; a.pa = x_part; a.ne = x_neg;
+  a.ga = g_anchor; a.gp = g_pos; a.gq = g_part; a.gn = g_neg;
+  a.B = B; a.D = D; a.prm = *prm; a.reduction = reduction;
+  a.saved = const_cast<float*>(saved); a.grad_out = grad_out;
+  return quad_dispatch(K_BWD, a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int qst_quadruplet_fwd_bwd(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                                      int dtype, int64_t B, int64_t D, const qst_quad_params* prm, int reduction,
+                                      float upstream, float* loss_out,
+                                      void* g_anchor, void* g_pos, void* g_part, void* g_neg,
+                                      void* workspace, qst_stream_t stream) {
+  QST_CHECK_ARG(prm != nullptr, "quadruplet: null params");
+  QuadArgs a{};
+  a.a = x_anchor; a.po = x_pos; a.pa = x_part; a.ne = x_neg;
+  a.ga = g_anchor; a.gp = g_pos; a.gq = g_part; a.gn = g_neg;
+  a.B = B; a.D = D; a.prm = *prm; a.reduction = reduction; a.upstream = upstream;
+  a.loss_out = loss_out; a.ws = reinterpret_cast<QuadWorkspace*>(workspace);
+  return quad_dispatch(K_FUSED, a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}

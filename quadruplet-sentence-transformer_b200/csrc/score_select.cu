@@ -1,0 +1,458 @@
+// K2: query-by-corpus scoring on the 5th-gen tensor cores with a streaming top-k' selection in
+// the epilogue.  The [Q, N] score matrix never reaches HBM.
+//
+// Replaces, per corpus shard, the hot loop of sentence-transformers 2.2.2
+// InformationRetrievalEvaluator.compute_metrices (constructed at
+// /root/reference/ir_evauation_script.py:107-123, models/evaluators.py:572-588):
+//     pair_scores = score_function(query_embeddings, sub_corpus_embeddings)   # torch.mm
+//     torch.topk(pair_scores, min(max_k, chunk), dim=1, largest=True, sorted=False)
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0      TMA producer: 128x64 query tile + 256x64 corpus tile per k-block into a
+//               4-stage 128B-swizzled smem ring (mbarrier full/empty pipeline)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) x4 per k-block,
+//               accumulating in TMEM; two 256-column accumulators are double-buffered so the
+//               epilogue of tile t overlaps the MMAs of tile t+1
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: thread r of the CTA owns query row r of the tile (TMEM lane r);
+//               tcgen05.ld 32 columns at a time, reject against the row's running threshold
+//               (k'-th best score seen), append survivors to the row's candidate buffer,
+//               warp-cooperative radix-select compaction when a buffer fills up.
+//
+// Work decomposition: the corpus is cut into `stripes` of `tiles_per_stripe` 256-row tiles; a
+// work unit is (stripe, 128-query tile).  Units are ordered stripe-major so the CTAs running at
+// the same time walk the same corpus stripe -> every corpus tile is fetched from HBM once and
+// re-read from L2 by the other query tiles.  Thresholds are shared between units of the same
+// query row through a global hint array (atomicMax), which removes the cold start of later units.
+#include "qst_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace qst {
+
+constexpr int BM = 128;          // query rows per tile  (UMMA M)
+constexpr int BN = 256;          // corpus rows per tile (UMMA N)
+constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int kScoreThreads = 256;
+constexpr uint32_t A_BYTES = BM * BK * 2;
+constexpr uint32_t B_BYTES = BN * BK * 2;
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t TMEM_COLS = 512;  // 2 accumulators x 256 fp32 columns
+constexpr size_t kScoreSmemBytes = (size_t)STAGES * STAGE_BYTES + 1024;  // + alignment slack
+
+struct ScoreParams {
+  int Q, N, num_kb;
+  int m_tiles, n_tiles, stripes, tiles_per_stripe, units;
+  int kprime, cap;
+  uint32_t* thr_hint;  // [m_tiles*BM] ordered keys, 0 = no threshold yet
+  int* unit_cnt;       // [units*BM]
+  uint2* unit_cand;    // [units*BM*cap]  (key, corpus row)
+  float* dense_out;    // dense mode only: [Q, N]
+};
+
+// ------------------------------------------------------------------------------------------
+// Warp-cooperative exact selection of the k-th largest key of buf[0..n) (keys in .x) followed by
+// an in-place compaction that keeps exactly k entries (all keys > T and enough == T).
+// Returns T.  hist: 256 ints of warp-private shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_select_compact(uint2* __restrict__ buf, int n, int k, int* hist, int lane) {
+  uint32_t prefix = 0, mask = 0;
+  int krem = k;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const uint32_t key = buf[i].x;
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncwarp();
+    int c[8];
+    int ls = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; ls += c[i]; }
+    // above = number of matching keys in bins owned by higher lanes (inclusive suffix - own)
+    int incl = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    const int above = incl - ls;
+    const bool mine = (above < krem) && (krem <= above + ls);
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int src = 31 - __clz(who);  // exactly one lane satisfies it when n >= krem
+    int digit = 0, cnt_above = 0;
+    if (lane == src) {
+      int run = above;
+#pragma unroll
+      for (int i = 7; i >= 0; --i) {
+        if (run < krem && krem <= run + c[i]) { digit = lane * 8 + i; cnt_above = run; }
+        run += c[i];
+      }
+    }
+    digit = __shfl_sync(0xffffffffu, digit, src);
+    cnt_above = __shfl_sync(0xffffffffu, cnt_above, src);
+    krem -= cnt_above;
+    prefix |= (uint32_t)digit << shift;
+    mask |= 255u << shift;
+    __syncwarp();
+  }
+  const uint32_t T = prefix;
+  // in-place stable compaction, 32 entries per step (reads of a step precede its writes)
+  int w = 0, eq_taken = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    uint2 e = make_uint2(0u, 0u);
+    if (i < n) e = buf[i];
+    const bool gt = (i < n) && (e.x > T);
+    const bool eq = (i < n) && (e.x == T);
+    const unsigned eqm = __ballot_sync(0xffffffffu, eq);
+    const bool keep = gt || (eq && (eq_taken + __popc(eqm & lt) < krem));
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) buf[w + __popc(km & lt)] = e;
+    w += __popc(km);
+    eq_taken += __popc(eqm);
+  }
+  __syncwarp();
+  return T;
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                    const ScoreParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[STAGES];
+  __shared__ __align__(8) uint64_t s_empty[STAGES];
+  __shared__ __align__(8) uint64_t s_tmem_full[2];
+  __shared__ __align__(8) uint64_t s_tmem_empty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_hist[4][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // 128B swizzle needs 1024-byte aligned stage bases
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&s_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(ptx::smem_u32(&s_tmem_full[a]), 1);
+      ptx::mbar_init(ptx::smem_u32(&s_tmem_empty[a]), 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // ============================== TMA producer ==============================
+    uint32_t stage = 0, phase = 0;
+    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+      const int s = u / P.m_tiles, m = u - s * P.m_tiles;
+      const int t0 = s * P.tiles_per_stripe;
+      const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
+          const uint32_t full = ptx::smem_u32(&s_full[stage]);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(full, STAGE_BYTES);
+          // queries are re-read by every corpus tile (keep in L2); a corpus tile is re-read by the
+          // other query tiles walking the same stripe (normal priority)
+          ptx::tma_load_2d(sa, &tmap_q, full, kb * BK, m * BM, ptx::kEvictLast);
+          ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full, kb * BK, t * BN, ptx::kEvictNormal);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ============================== MMA issuer ================================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+      const int s = u / P.m_tiles;
+      const int t0 = s * P.tiles_per_stripe;
+      const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait(ptx::smem_u32(&s_tmem_empty[acc]), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+          const uint64_t db = ptx::make_sw128_kmajor_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the addr>>4 field
+            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(ptx::smem_u32(&s_empty[stage]));  // frees the smem slot when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&s_tmem_full[acc]));  // accumulator ready for the epilogue
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==================================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row_in_tile = quarter * 32 + lane;
+    int* hist = s_hist[quarter];
+    uint32_t acc = 0, acc_phase = 0;
+    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+      const int s = u / P.m_tiles, m = u - s * P.m_tiles;
+      const int t0 = s * P.tiles_per_stripe;
+      const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
+      const int grow = m * BM + row_in_tile;
+      const bool row_ok = grow < P.Q;
+      float thr = row_ok ? -INFINITY : INFINITY;
+      int cnt = 0;
+      uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * BM + row_in_tile) * (size_t)P.cap;
+      for (int t = t0; t < t1; ++t) {
+        if (!DENSE && row_ok) {  // pick up thresholds published by other units of this row
+          const uint32_t hk = __ldcg(&P.thr_hint[grow]);
+          if (hk != 0u) thr = fmaxf(thr, key_to_float(hk));
+        }
+        ptx::mbar_wait(ptx::smem_u32(&s_tmem_full[acc]), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + chunk * 32, v);
+          ptx::tmem_ld_wait();
+          if (chunk == BN / 32 - 1) {
+            // every column of this accumulator is now in registers: hand TMEM back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
+          }
+          const int col0 = t * BN + chunk * 32;
+          if (col0 + 32 > P.N) {  // ragged last tile: columns >= N were zero-filled by TMA
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j >= P.N) v[j] = 0xff800000u;  // -inf
+          }
+          if (DENSE) {
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < P.N) P.dense_out[(size_t)grow * P.N + col0 + j] = __uint_as_float(v[j]);
+            }
+          } else {
+            float mx = __uint_as_float(v[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+            if (mx > thr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float sc = __uint_as_float(v[j]);
+                if (sc > thr) {
+                  my_buf[cnt] = make_uint2(float_to_key(sc), (uint32_t)(col0 + j));
+                  ++cnt;
+                }
+              }
+            }
+            // keep room for the next chunk's worst case (32 appends)
+            unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
+            while (need) {
+              const int r = __ffs(need) - 1;
+              need &= need - 1;
+              const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
+              const int n = __shfl_sync(0xffffffffu, cnt, r);
+              const uint32_t T = warp_select_compact(reinterpret_cast<uint2*>(bp), n, P.kprime, hist, lane);
+              if (lane == r) {
+                cnt = P.kprime;
+                thr = fmaxf(thr, key_to_float(T));
+                atomicMax(&P.thr_hint[grow], T);
+              }
+            }
+          }
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (!DENSE) P.unit_cnt[(size_t)u * BM + row_in_tile] = cnt;
+    }
+  }
+
+  // ------------------------------ teardown ------------------------------
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// bf16 [rows, d_pad] row-major -> tiles of box_rows x 64 columns, 128B swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pad, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return QST_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return QST_ERR_CUDA; }
+  return QST_OK;
+}
+
+static int launch_score(bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P, int64_t d_pad,
+                        int grid, cudaStream_t st) {
+  CUtensorMap tq, tc;
+  int rc = make_tmap(&tq, q_bf16, P.Q, d_pad, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tc, c_bf16, P.N, d_pad, BN);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    QST_CUDA(cudaFuncSetAttribute(score_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kScoreSmemBytes));
+    QST_CUDA(cudaFuncSetAttribute(score_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kScoreSmemBytes));
+    attr_done = true;
+  }
+  if (dense) score_select_kernel<true><<<grid, kScoreThreads, kScoreSmemBytes, st>>>(tq, tc, P);
+  else score_select_kernel<false><<<grid, kScoreThreads, kScoreSmemBytes, st>>>(tq, tc, P);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+static int device_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return sms;
+}
+
+}  // namespace qst
+
+using namespace qst;
+
+extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kprime, int score, int sm_count,
+                                  qst_topk_plan* plan) {
+  QST_CHECK_ARG(plan != nullptr, "plan_make: null plan");
+  QST_CHECK_ARG(Q >= 1 && N >= 1 && D >= 1, "plan_make: bad shape Q=%lld N=%lld D=%lld", (long long)Q, (long long)N,
+                (long long)D);
+  QST_CHECK_ARG(Q < (1ll << 31) - BM && N < (1ll << 31) - BN, "plan_make: Q and N must fit in int32");
+  QST_CHECK_ARG(k >= 1 && k <= 1024, "plan_make: k must be in [1, 1024], %d given", k);
+  QST_CHECK_ARG(score == QST_SCORE_COS || score == QST_SCORE_DOT, "plan_make: score %d not supported by the tensor-core path", score);
+  if (sm_count <= 0) sm_count = device_sm_count();
+  if (sm_count <= 0) sm_count = 148;
+  if (kprime <= 0) {
+    // head-room so that the bf16 ordering error cannot push a true top-k document out of the
+    // candidate set (DESIGN.md "certificate"): k + max(k/2, 32), in steps of 32
+    int extra = k / 2 > 32 ? k / 2 : 32;
+    kprime = (int)round_up(k + extra, 32);
+  }
+  kprime = (int)round_up(kprime, 32);
+  QST_CHECK_ARG(kprime >= k && kprime <= 2048, "plan_make: kprime %d out of range [k, 2048]", kprime);
+  memset(plan, 0, sizeof(*plan));
+  plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim(D);
+  plan->k = k; plan->kprime = kprime; plan->cap = 2 * kprime;
+  plan->score = score;
+  plan->m_tiles = (int)ceil_div(Q, BM);
+  plan->n_tiles = (int)ceil_div(N, BN);
+  // stripes: minimise  waves * (tiles_per_stripe + cold-start cost)  over S
+  const int r_min = 4;
+  int s_max = plan->n_tiles / r_min;
+  if (s_max < 1) s_max = 1;
+  if (s_max > 64) s_max = 64;
+  double best = 1e300;
+  int best_s = 1;
+  for (int S = 1; S <= s_max; ++S) {
+    const int R = (int)ceil_div(plan->n_tiles, S);
+    const int S_eff = (int)ceil_div(plan->n_tiles, R);  // stripes actually non-empty
+    const int64_t units = (int64_t)plan->m_tiles * S_eff;
+    const int64_t waves = ceil_div(units, sm_count);
+    const double cost = (double)waves * ((double)R + 2.0);
+    if (cost < best - 1e-9) { best = cost; best_s = S_eff; }
+  }
+  plan->tiles_per_stripe = (int)ceil_div(plan->n_tiles, best_s);
+  plan->stripes = (int)ceil_div(plan->n_tiles, plan->tiles_per_stripe);
+  plan->units = plan->m_tiles * plan->stripes;
+  plan->grid = plan->units < sm_count ? plan->units : sm_count;
+  size_t off = 0;
+  plan->off_thr = off;  off += round_up((size_t)plan->m_tiles * BM * sizeof(uint32_t), 256);
+  plan->off_cnt = off;  off += round_up((size_t)plan->units * BM * sizeof(int), 256);
+  plan->off_cand = off; off += (size_t)plan->units * BM * (size_t)plan->cap * sizeof(uint2);
+  plan->ws_bytes = off;
+  return QST_OK;
+}
+
+extern "C" int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
+                                qst_stream_t stream) {
+  QST_CHECK_ARG(plan && q_bf16 && c_bf16 && workspace, "score_select: null argument");
+  QST_CHECK_ARG((reinterpret_cast<uintptr_t>(q_bf16) & 15u) == 0 && (reinterpret_cast<uintptr_t>(c_bf16) & 15u) == 0,
+                "score_select: operands must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  ScoreParams P{};
+  P.Q = (int)plan->Q; P.N = (int)plan->N; P.num_kb = (int)(plan->D_pad / BK);
+  P.m_tiles = plan->m_tiles; P.n_tiles = plan->n_tiles; P.stripes = plan->stripes;
+  P.tiles_per_stripe = plan->tiles_per_stripe; P.units = plan->units;
+  P.kprime = plan->kprime; P.cap = plan->cap;
+  P.thr_hint = reinterpret_cast<uint32_t*>(ws + plan->off_thr);
+  P.unit_cnt = reinterpret_cast<int*>(ws + plan->off_cnt);
+  P.unit_cand = reinterpret_cast<uint2*>(ws + plan->off_cand);
+  QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * BM * sizeof(uint32_t), st));
+  return launch_score(false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
+}
+
+extern "C" int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad, float* out,
+                               qst_stream_t stream) {
+  QST_CHECK_ARG(q_bf16 && c_bf16 && out, "score_dense: null argument");
+  QST_CHECK_ARG(Q >= 1 && N >= 1 && D_pad >= BK && D_pad % BK == 0, "score_dense: bad shape");
+  ScoreParams P{};
+  P.Q = (int)Q; P.N = (int)N; P.num_kb = (int)(D_pad / BK);
+  P.m_tiles = (int)ceil_div(Q, BM); P.n_tiles = (int)ceil_div(N, BN);
+  P.stripes = 1; P.tiles_per_stripe = P.n_tiles; P.units = P.m_tiles;
+  P.dense_out = out;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int grid = P.units < sms ? P.units : sms;
+  return launch_score(true, q_bf16, c_bf16, P, D_pad, grid, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,240 @@
+"""Drop-in ``InformationRetrievalEvaluator`` running the B200 kernels.
+
+Keeps the constructor keywords, ``__call__`` (``SentenceEvaluator`` protocol) and
+``compute_metrices`` of sentence-transformers 2.2.2 ``InformationRetrievalEvaluator`` exactly as the
+reference uses them:
+
+* construction ......... ``/root/reference/ir_evauation_script.py:107-123``,
+  ``models/evaluators.py:572-588``
+* call ................. ``ir_evauation_script.py:130-131`` (``evaluator(model=..., output_path=...)``),
+  and inside ``SequentialEvaluator`` (``models/evaluators.py:614``)
+* score functions ...... ``Dict[str, Callable]`` (``models/evaluators.py:545-546``); this module's
+  ``cos_sim`` / ``dot_score`` select the fused tensor-core path
+
+What changes underneath: embeddings stay on the GPU, scoring + top-k never materialise the
+[Q, N] matrix (K2/K3), per-query metrics run on the device (K4); no Python per-hit lists.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Callable, Dict, List, Optional, Set
+
+import numpy as np
+import torch
+
+from . import _lib, metrics, scoring
+from .scoring import cos_sim, dot_score
+
+logger = logging.getLogger(__name__)
+
+
+class InformationRetrievalEvaluator:
+    def __init__(self,
+                 queries: Dict[str, str],
+                 corpus: Dict[str, str],
+                 relevant_docs: Dict[str, Set[str]],
+                 corpus_chunk_size: int = 50000,
+                 mrr_at_k: List[int] = [10],
+                 ndcg_at_k: List[int] = [10],
+                 accuracy_at_k: List[int] = [1, 3, 5, 10],
+                 precision_recall_at_k: List[int] = [1, 3, 5, 10],
+                 map_at_k: List[int] = [100],
+                 show_progress_bar: bool = False,
+                 batch_size: int = 32,
+                 name: str = '',
+                 write_csv: bool = True,
+                 score_functions: Dict[str, Callable] = None,
+                 main_score_function: str = None,
+                 device: Optional[str] = None,
+                 kprime: int = 0):
+        if score_functions is None:
+            score_functions = {'cos_sim': cos_sim, 'dot_score': dot_score}
+        for fn_name, fn in score_functions.items():
+            if scoring.score_name_of(fn) is None:
+                raise TypeError(
+                    f"score function {fn_name!r} is not one of this package's fused score functions "
+                    f"(cos_sim, dot_score); arbitrary callables would need the dense [Q, N] matrix this "
+                    f"implementation never builds")
+        self.queries_ids = [qid for qid in queries if qid in relevant_docs and len(relevant_docs[qid]) > 0]
+        self.queries = [queries[qid] for qid in self.queries_ids]
+        self.corpus_ids = list(corpus.keys())
+        self.corpus = [corpus[cid] for cid in self.corpus_ids]
+        self.relevant_docs = relevant_docs
+        self.corpus_chunk_size = corpus_chunk_size
+        self.mrr_at_k, self.ndcg_at_k = mrr_at_k, ndcg_at_k
+        self.accuracy_at_k, self.precision_recall_at_k, self.map_at_k = accuracy_at_k, precision_recall_at_k, map_at_k
+        self.show_progress_bar = show_progress_bar
+        self.batch_size = batch_size
+        self.name = name
+        self.write_csv = write_csv
+        self.score_functions = score_functions
+        self.score_function_names = sorted(score_functions.keys())
+        self.main_score_function = main_score_function
+        self.device = device
+        self.kprime = kprime
+
+        self.csv_file = "Information-Retrieval_evaluation" + ("_" + name if name else "") + "_results.csv"
+        self.csv_headers = ["epoch", "steps"] + [h for fn in self.score_function_names for h in self._columns(fn)]
+
+        # relevance as corpus positions; ids missing from the corpus keep a slot (position >= N)
+        # because the reference divides by len(relevant_docs[qid]) regardless
+        pos_of = {cid: i for i, cid in enumerate(self.corpus_ids)}
+        n = len(self.corpus_ids)
+        self._relevant_positions = []
+        for qid in self.queries_ids:
+            row, missing = [], 0
+            for cid in relevant_docs[qid]:
+                p = pos_of.get(cid)
+                if p is None:
+                    p = n + missing
+                    missing += 1
+                row.append(p)
+            self._relevant_positions.append(row)
+        self._csr_cache = {}
+        self.last_margins = {}
+
+    def _columns(self, fn: str) -> List[str]:
+        cols = ["{}-Accuracy@{}".format(fn, k) for k in self.accuracy_at_k]
+        for k in self.precision_recall_at_k:
+            cols += ["{}-Precision@{}".format(fn, k), "{}-Recall@{}".format(fn, k)]
+        cols += ["{}-MRR@{}".format(fn, k) for k in self.mrr_at_k]
+        cols += ["{}-NDCG@{}".format(fn, k) for k in self.ndcg_at_k]
+        cols += ["{}-MAP@{}".format(fn, k) for k in self.map_at_k]
+        return cols
+
+    def _values(self, s: Dict[str, Dict[int, float]]) -> list:
+        row = [s['accuracy@k'][k] for k in self.accuracy_at_k]
+        for k in self.precision_recall_at_k:
+            row += [s['precision@k'][k], s['recall@k'][k]]
+        row += [s['mrr@k'][k] for k in self.mrr_at_k]
+        row += [s['ndcg@k'][k] for k in self.ndcg_at_k]
+        row += [s['map@k'][k] for k in self.map_at_k]
+        return row
+
+    # ---- SentenceEvaluator protocol ----------------------------------------------------------
+    def __call__(self, model, output_path: str = None, epoch: int = -1, steps: int = -1, *args, **kwargs) -> float:
+        if epoch != -1:
+            out_txt = " after epoch {}:".format(epoch) if steps == -1 else " in epoch {} after {} steps:".format(epoch, steps)
+        else:
+            out_txt = ":"
+        logger.info("Information Retrieval Evaluation on " + self.name + " dataset" + out_txt)
+        scores = self.compute_metrices(model, *args, **kwargs)
+        if output_path is not None and self.write_csv:
+            csv_path = os.path.join(output_path, self.csv_file)
+            is_new = not os.path.isfile(csv_path)
+            with open(csv_path, mode="w" if is_new else "a", encoding="utf-8") as f:
+                if is_new:
+                    f.write(",".join(self.csv_headers) + "\n")
+                row = [epoch, steps] + [v for fn in self.score_function_names for v in self._values(scores[fn])]
+                f.write(",".join(map(str, row)) + "\n")
+        if self.main_score_function is None:
+            return max(scores[fn]['map@k'][max(self.map_at_k)] for fn in self.score_function_names)
+        return scores[self.main_score_function]['map@k'][max(self.map_at_k)]
+
+    @property
+    def max_k(self) -> int:
+        return max(max(self.mrr_at_k), max(self.ndcg_at_k), max(self.accuracy_at_k),
+                   max(self.precision_recall_at_k), max(self.map_at_k))
+
+    def _cuda_device(self, *tensors) -> torch.device:
+        if self.device is not None:
+            return torch.device(self.device)
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                return t.device
+        if not torch.cuda.is_available():
+            raise _lib.QstError("InformationRetrievalEvaluator needs a CUDA device (no CPU fallback)")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _encode(self, model, sentences, dev) -> torch.Tensor:
+        emb = model.encode(sentences, show_progress_bar=False, batch_size=self.batch_size, convert_to_tensor=True)
+        if not isinstance(emb, torch.Tensor):
+            emb = torch.as_tensor(np.asarray(emb))
+        return emb.to(dev, non_blocking=True)
+
+    def rank(self, model, corpus_model=None, corpus_embeddings: torch.Tensor = None) -> Dict[str, scoring.TopkResult]:
+        """Top-``max_k`` ranking per score function: device tensors, global corpus positions."""
+        if corpus_model is None:
+            corpus_model = model
+        dev = self._cuda_device(corpus_embeddings)
+        lib = _lib.load()
+        n_corpus = len(self.corpus)
+        k = min(self.max_k, n_corpus)
+        with torch.cuda.device(dev):
+            q_emb = self._encode(model, self.queries, dev)
+            out = {}
+            prepared_q = {}
+            partial = {fn: [] for fn in self.score_functions}
+            for start in range(0, n_corpus, self.corpus_chunk_size):
+                end = min(start + self.corpus_chunk_size, n_corpus)
+                if corpus_embeddings is None:
+                    sub = self._encode(corpus_model, self.corpus[start:end], dev)
+                else:
+                    sub = corpus_embeddings[start:end].to(dev, non_blocking=True)
+                for fn_name, fn in self.score_functions.items():
+                    score = scoring.score_name_of(fn)
+                    if score not in prepared_q:
+                        prepared_q[score] = scoring.prepare_rows(q_emb, normalize=(score == "cos_sim"))
+                    index = scoring.CorpusIndex(sub, score, idx_offset=start)
+                    kk = min(k, end - start)
+                    res = scoring.topk(None, index, kk, self.kprime, exact=True, prepared_queries=prepared_q[score])
+                    partial[fn_name].append(res)
+            for fn_name, parts in partial.items():
+                if len(parts) == 1 and parts[0].values.shape[1] == k:
+                    out[fn_name] = parts[0]
+                    continue
+                # K6: merge the per-chunk lists (the reference concatenates them and sorts)
+                Q = q_emb.shape[0]
+                vals = torch.full((len(parts), Q, k), float("-inf"), dtype=torch.float32, device=dev)
+                idx = torch.full((len(parts), Q, k), -1, dtype=torch.int64, device=dev)
+                for g, r in enumerate(parts):
+                    vals[g, :, :r.values.shape[1]] = r.values
+                    idx[g, :, :r.indices.shape[1]] = r.indices
+                mv = torch.empty((Q, k), dtype=torch.float32, device=dev)
+                mi = torch.empty((Q, k), dtype=torch.int64, device=dev)
+                _lib.check(lib.qst_merge_topk(vals.data_ptr(), idx.data_ptr(), len(parts), Q, k, mv.data_ptr(),
+                                              mi.data_ptr(), _lib.stream_ptr(dev)))
+                margin = torch.stack([r.margin for r in parts]).amin(dim=0)
+                out[fn_name] = scoring.TopkResult(mv, mi, margin, None)
+        return out
+
+    def compute_metrices(self, model, corpus_model=None, corpus_embeddings: torch.Tensor = None) -> Dict[str, dict]:
+        ranked = self.rank(model, corpus_model, corpus_embeddings)
+        logger.info("Queries: {}".format(len(self.queries)))
+        logger.info("Corpus: {}\n".format(len(self.corpus)))
+        scores = {}
+        for fn_name, res in ranked.items():
+            self.last_margins[fn_name] = res.margin
+            scores[fn_name] = self.compute_metrics_from_ranking(res.indices)
+        for fn_name in self.score_function_names:
+            logger.info("Score-Function: {}".format(fn_name))
+            self.output_scores(scores[fn_name])
+        return scores
+
+    def compute_metrics_from_ranking(self, ranked_idx: torch.Tensor) -> Dict[str, Dict[int, float]]:
+        """K4 + the reference's cross-query reductions (``compute_metrics`` of ST 2.2.2)."""
+        dev = ranked_idx.device
+        key = (dev.type, dev.index)
+        if key not in self._csr_cache:
+            self._csr_cache[key] = metrics.relevance_csr(self._relevant_positions, dev)
+        rowptr, cols = self._csr_cache[key]
+        ks = sorted(set(self.accuracy_at_k) | set(self.precision_recall_at_k) | set(self.mrr_at_k)
+                    | set(self.ndcg_at_k) | set(self.map_at_k))
+        per_query = metrics.per_query_metrics(ranked_idx, rowptr, cols, ks).cpu().numpy()
+        return metrics.reduce_like_reference(per_query, ks, self.accuracy_at_k, self.precision_recall_at_k,
+                                             self.mrr_at_k, self.ndcg_at_k, self.map_at_k)
+
+    def output_scores(self, scores):
+        for k in scores['accuracy@k']:
+            logger.info("Accuracy@{}: {:.2f}%".format(k, scores['accuracy@k'][k] * 100))
+        for k in scores['precision@k']:
+            logger.info("Precision@{}: {:.2f}%".format(k, scores['precision@k'][k] * 100))
+        for k in scores['recall@k']:
+            logger.info("Recall@{}: {:.2f}%".format(k, scores['recall@k'][k] * 100))
+        for k in scores['mrr@k']:
+            logger.info("MRR@{}: {:.4f}".format(k, scores['mrr@k'][k]))
+        for k in scores['ndcg@k']:
+            logger.info("NDCG@{}: {:.4f}".format(k, scores['ndcg@k'][k]))
+        for k in scores['map@k']:
+            logger.info("MAP@{}: {:.4f}".format(k, scores['map@k'][k]))

@@ -1,0 +1,238 @@
+"""Query-by-corpus scoring + exact top-k on B200 (K1 prep, K2 tensor-core select, K3 rescore).
+
+Host-side mirror of what sentence-transformers 2.2.2 ``InformationRetrievalEvaluator.
+compute_metrices`` does per corpus chunk -- ``score_function(q, c)`` then ``torch.topk`` -- for the
+score functions the reference wires in at ``/root/reference/ir_evauation_script.py:70``
+(``cos_sim``, ``dot_score``).  The corpus stays resident in HBM as a ``CorpusIndex`` (fp32 master,
+normalised bf16 operand, inverse norms); ``topk`` runs the three kernels on the current stream.
+
+Nothing here falls back to PyTorch arithmetic: CPU tensors raise, a missing ``libqst.so`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+SCORE_CODES = {"cos_sim": _lib.QST_SCORE_COS, "dot_score": _lib.QST_SCORE_DOT}
+
+
+def cos_sim(a, b):
+    """Marker + dense entry for the ``cos_sim`` score function (``ir_evauation_script.py:70``).
+
+    The evaluator recognises this callable and runs the fused path (the [Q, N] matrix is never
+    materialised).  Called directly it returns the dense fp32 cosine matrix computed from the
+    exact rescoring kernel, for the small inputs the reference uses it on elsewhere.
+    """
+    return _dense_scores(a, b, "cos_sim")
+
+
+def dot_score(a, b):
+    """Marker + dense entry for ``dot_score`` (``ir_evauation_script.py:70``)."""
+    return _dense_scores(a, b, "dot_score")
+
+
+cos_sim.qst_score = "cos_sim"
+dot_score.qst_score = "dot_score"
+
+
+def score_name_of(fn) -> Optional[str]:
+    """Name of the fused score function behind a callable, or None for a foreign callable."""
+    return getattr(fn, "qst_score", None)
+
+
+def _as_2d_cuda(x) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        x = torch.tensor(x)
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    _lib.require_cuda(x)
+    return x
+
+
+@dataclass
+class PreparedRows:
+    f32: torch.Tensor        # [n, D] fp32 master (contiguous)
+    bf16: torch.Tensor       # [n, D_pad] bf16 tensor-core operand
+    inv_norm: torch.Tensor   # [n] 1/max(||x||, 1e-12)
+    sq_norm: torch.Tensor    # [n] ||x||^2
+    err: torch.Tensor        # [n] ||bf16(row) - row||
+    stats: torch.Tensor      # [2] max err, max used norm
+
+    @property
+    def n(self) -> int:
+        return self.f32.shape[0]
+
+    @property
+    def d(self) -> int:
+        return self.f32.shape[1]
+
+
+def prepare_rows(x: torch.Tensor, normalize: bool) -> PreparedRows:
+    """K1 (``qst_prep_rows``): norms, optional normalisation, bf16 cast, zero padding."""
+    lib = _lib.load()
+    x = _as_2d_cuda(x)
+    if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    n, d = x.shape
+    dev = x.device
+    d_pad = lib.qst_padded_dim(d)
+    with torch.cuda.device(dev):
+        bf = torch.empty((n, d_pad), dtype=torch.bfloat16, device=dev)
+        inv = torch.empty(n, dtype=torch.float32, device=dev)
+        sq = torch.empty(n, dtype=torch.float32, device=dev)
+        err = torch.empty(n, dtype=torch.float32, device=dev)
+        stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.qst_prep_rows(x.data_ptr(), _lib.dtype_code(x.dtype), n, d, int(normalize), bf.data_ptr(),
+                                     inv.data_ptr(), sq.data_ptr(), err.data_ptr(), stats.data_ptr(),
+                                     _lib.stream_ptr(dev)))
+    f32 = x if x.dtype == torch.float32 else x.float()
+    return PreparedRows(f32, bf, inv, sq, err, stats)
+
+
+class CorpusIndex:
+    """One corpus shard resident in HBM, prepared once for a given score function.
+
+    ``idx_offset`` is the global id of the shard's first row (corpus-sharded retrieval,
+    SURVEY.md section 8e).
+    """
+
+    def __init__(self, corpus_embeddings: torch.Tensor, score: str = "cos_sim", idx_offset: int = 0):
+        if score not in SCORE_CODES:
+            raise ValueError(f"score must be one of {sorted(SCORE_CODES)}, {score} given")
+        self.score = score
+        self.idx_offset = int(idx_offset)
+        self.rows = prepare_rows(corpus_embeddings, normalize=(score == "cos_sim"))
+
+    @property
+    def n(self) -> int:
+        return self.rows.n
+
+    @property
+    def d(self) -> int:
+        return self.rows.d
+
+    @property
+    def device(self) -> torch.device:
+        return self.rows.f32.device
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def make_plan(Q: int, N: int, D: int, k: int, kprime: int = 0, score: str = "cos_sim",
+              sm_count: int = 0) -> _lib.TopkPlan:
+    plan = _lib.TopkPlan()
+    _lib.check(_lib.load().qst_topk_plan_make(Q, N, D, k, kprime, SCORE_CODES[score], sm_count, C.byref(plan)))
+    return plan
+
+
+@dataclass
+class TopkResult:
+    values: torch.Tensor    # [Q, k] fp32, descending
+    indices: torch.Tensor   # [Q, k] int64 global corpus ids, -1 where the shard has fewer than k rows
+    margin: torch.Tensor    # [Q] fp32 certificate (> 0: proven exact; +inf after an exact re-scan)
+    plan: _lib.TopkPlan
+
+
+def topk(queries: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0, exact: bool = True,
+         prepared_queries: Optional[PreparedRows] = None) -> TopkResult:
+    """Exact top-``k`` corpus rows per query under ``index.score``.
+
+    bf16 tensor-core pass keeps ``kprime`` candidates per query, fp32 rescoring orders them; with
+    ``exact=True`` queries whose certificate fails are re-scanned in fp32 on the device.
+    """
+    lib = _lib.load()
+    pq = prepared_queries if prepared_queries is not None else prepare_rows(queries, index.score == "cos_sim")
+    if pq.d != index.d:
+        raise ValueError(f"query dim {pq.d} != corpus dim {index.d}")
+    dev = index.device
+    Q, N, D = pq.n, index.n, index.d
+    if Q == 0:
+        z = torch.empty((0, k), device=dev)
+        return TopkResult(z, z.long(), torch.empty(0, device=dev), None)
+    plan = make_plan(Q, N, D, k, kprime, index.score)
+    st = _lib.stream_ptr(dev)
+    cos = index.score == "cos_sim"
+    with torch.cuda.device(dev):
+        ws = _workspace(plan.ws_bytes, dev, "select")
+        vals = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        margin = torch.empty(Q, dtype=torch.float32, device=dev)
+        c = index.rows
+        _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), c.bf16.data_ptr(), ws.data_ptr(), st))
+        _lib.check(lib.qst_finalize_topk(C.byref(plan), ws.data_ptr(), pq.f32.data_ptr(),
+                                         pq.inv_norm.data_ptr() if cos else None, pq.err.data_ptr(),
+                                         c.f32.data_ptr(), c.inv_norm.data_ptr() if cos else None,
+                                         c.stats.data_ptr(), index.idx_offset, vals.data_ptr(), idx.data_ptr(),
+                                         margin.data_ptr(), st))
+        if exact:
+            scratch = _workspace(lib.qst_exact_rescan_workspace_bytes(Q, k), dev, "rescan")
+            _lib.check(lib.qst_exact_rescan(Q, N, D, k, SCORE_CODES[index.score], pq.f32.data_ptr(),
+                                            pq.inv_norm.data_ptr() if cos else None, c.f32.data_ptr(),
+                                            c.inv_norm.data_ptr() if cos else None, index.idx_offset,
+                                            vals.data_ptr(), idx.data_ptr(), margin.data_ptr(),
+                                            scratch.data_ptr(), st))
+    return TopkResult(vals, idx, margin, plan)
+
+
+def dense_tensorcore_scores(q_bf16: torch.Tensor, c_bf16: torch.Tensor) -> torch.Tensor:
+    """Raw bf16 tensor-core scores [Q, N] (``qst_score_dense``); validation aid for K2."""
+    lib = _lib.load()
+    _lib.require_cuda(q_bf16, c_bf16)
+    Q, d_pad = q_bf16.shape
+    N = c_bf16.shape[0]
+    out = torch.empty((Q, N), dtype=torch.float32, device=q_bf16.device)
+    with torch.cuda.device(q_bf16.device):
+        _lib.check(lib.qst_score_dense(q_bf16.data_ptr(), Q, c_bf16.data_ptr(), N, d_pad, out.data_ptr(),
+                                       _lib.stream_ptr(q_bf16.device)))
+    return out
+
+
+def _dense_scores(a, b, score: str) -> torch.Tensor:
+    """Dense fp32 [Q, N] scores through the exact path: top-N of every query, scattered back.
+
+    Only meant for the small direct uses of ``cos_sim`` in the reference (e.g.
+    ``dataset/positive_examples_selection.py:55``); N is limited to 1024 columns.
+    """
+    a, b = _as_2d_cuda(a), _as_2d_cuda(b)
+    N = b.shape[0]
+    if N > 1024:
+        raise ValueError("dense score matrices are limited to 1024 corpus rows; use topk()/the evaluator "
+                         "for retrieval-sized inputs (the [Q, N] matrix is never materialised there)")
+    res = topk(a, CorpusIndex(b, score), k=N, kprime=max(32, ((N + 31) // 32) * 32), exact=False)
+    out = torch.empty((a.shape[0], N), dtype=torch.float32, device=a.device)
+    out.scatter_(1, res.indices.clamp_min(0), res.values)
+    return out
+
+
+def topk_host(queries_host: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0,
+              exact: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """End-to-end call with HOST buffers: pinned queries in, pinned (values, indices) out.
+
+    This is the boundary ``bench.py`` times as ``e2e``: H2D copy of the query embeddings, K1 on the
+    queries, K2, K3, D2H copy of the ranking.
+    """
+    dev = index.device
+    q_dev = queries_host.to(dev, non_blocking=True)
+    res = topk(q_dev, index, k, kprime, exact)
+    vals = torch.empty(res.values.shape, dtype=torch.float32, pin_memory=True)
+    idx = torch.empty(res.indices.shape, dtype=torch.int64, pin_memory=True)
+    vals.copy_(res.values, non_blocking=True)
+    idx.copy_(res.indices, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return vals, idx

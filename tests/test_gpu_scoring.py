@@ -1,0 +1,264 @@
+"""Parity of the scoring / top-k / metrics kernels (K1-K4, K6) with the CPU oracle, through the
+C ABI.  Bars (BASELINE.json north_star): top-k indices identical to torch fp32 cos_sim+topk except
+ties within 1e-6; IR metric values bit-identical given identical rankings."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TIE = 1e-6
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def assert_same_ranking(got_idx, got_val, want_idx, want_val, what=""):
+    """Index-for-index equality, except inside groups of reference scores within TIE."""
+    got_idx, got_val = got_idx.cpu(), got_val.cpu()
+    torch.testing.assert_close(got_val, want_val, rtol=0, atol=2e-6, msg=lambda m: f"{what} scores: {m}")
+    mism = (got_idx != want_idx)
+    if not mism.any():
+        return 0
+    n_tie = 0
+    for q, j in mism.nonzero().tolist():
+        # the document we emitted at rank j must have a reference score within TIE of the
+        # reference's rank-j score (a tie swap), and must be part of the reference's top-k or tie
+        # with its last element
+        s_ref = float(want_val[q, j])
+        where = (want_idx[q] == got_idx[q, j]).nonzero()
+        if where.numel():
+            s_doc = float(want_val[q, where[0, 0]])
+        else:
+            s_doc = float(got_val[q, j])
+            assert abs(s_doc - float(want_val[q, -1])) <= 2 * TIE, f"{what}: q={q} rank={j} not in reference top-k"
+        assert abs(s_doc - s_ref) <= 2 * TIE, f"{what}: q={q} rank={j}: {s_doc} vs {s_ref} is not a tie"
+        n_tie += 1
+    return n_tie
+
+
+@pytest.mark.parametrize("Q,N,D", [(100, 700, 384), (128, 256, 64), (1, 1, 8), (257, 513, 100), (300, 5000, 768)])
+def test_tensorcore_scores_match_bf16_matmul(Q, N, D):
+    """K1 + K2 (dense debug epilogue): TMA/UMMA descriptors, swizzle, TMEM layout, ragged tiles."""
+    import qst_b200
+    from qst_b200 import scoring
+    g = torch.Generator().manual_seed(14)
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g)
+    pq = scoring.prepare_rows(q.to(_dev()), normalize=True)
+    pc = scoring.prepare_rows(c.to(_dev()), normalize=True)
+    # K1 against torch
+    qn = torch.nn.functional.normalize(q, p=2, dim=1)
+    assert pq.bf16.shape[1] % 64 == 0
+    torch.testing.assert_close(pq.bf16[:, :D].float().cpu(), qn.bfloat16().float(), rtol=0, atol=2 ** -8)
+    assert float(pq.bf16[:, D:].float().abs().max() if pq.bf16.shape[1] > D else 0.0) == 0.0
+    torch.testing.assert_close(pq.inv_norm.cpu(), 1 / q.norm(dim=1).clamp_min(1e-12), rtol=1e-6, atol=0)
+    torch.testing.assert_close(pq.sq_norm.cpu(), (q * q).sum(1), rtol=1e-5, atol=0)
+    err = (pq.bf16[:, :D].float() - (q.to(_dev()) * pq.inv_norm[:, None])).norm(dim=1)
+    torch.testing.assert_close(pq.err, err, rtol=1e-3, atol=1e-7)
+    # K2 against an fp32 matmul of the very same bf16 operands (products exact, fp32 accumulate)
+    got = scoring.dense_tensorcore_scores(pq.bf16, pc.bf16)
+    want = pq.bf16.float() @ pc.bf16.float().T
+    torch.testing.assert_close(got, want, rtol=0, atol=2e-5)
+
+
+def _oracle_topk(q, c, k, score="cos_sim", chunk=50000):
+    from oracle import ir_oracle
+    return ir_oracle.topk_dense(q, c, k, score, corpus_chunk_size=chunk)
+
+
+@pytest.mark.parametrize("Q,N,D,k", [(1000, 10000, 384, 10), (64, 3000, 768, 100), (200, 20000, 96, 100),
+                                     (5, 40, 16, 10), (130, 257, 33, 7)])
+@pytest.mark.parametrize("score", ["cos_sim", "dot_score"])
+def test_topk_matches_oracle(Q, N, D, k, score):
+    import qst_b200
+    g = torch.Generator().manual_seed(14 + Q)
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g) * (1.0 + torch.rand(N, 1, generator=g))   # varied norms
+    want_val, want_idx = _oracle_topk(q, c, k, score)
+    index = qst_b200.CorpusIndex(c.to(_dev()), score)
+    res = qst_b200.topk(q.to(_dev()), index, k)
+    if score == "dot_score":
+        scale = float(want_val.abs().max())
+        torch.testing.assert_close(res.values.cpu() / scale, want_val / scale, rtol=0, atol=2e-6)
+        assert (res.indices.cpu() == want_idx).float().mean() > 0.999
+    else:
+        assert_same_ranking(res.indices, res.values, want_idx, want_val, f"{score} {Q}x{N}x{D} k={k}")
+    assert bool((res.margin > 0).all()), "every query must end certified (after the exact re-scan if needed)"
+
+
+def test_topk_large_k_and_small_corpus():
+    """k up to the script default 900 (ir_evauation_script.py:163-173); corpus smaller than k."""
+    import qst_b200
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(20, 64, generator=g)
+    c = torch.randn(9000, 64, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, 900)
+    res = qst_b200.topk(q.to(_dev()), qst_b200.CorpusIndex(c.to(_dev())), 900)
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, "k=900")
+    # N < k: the reference returns min(max_k, len(chunk)) hits; we pad with -1 / -inf
+    res = qst_b200.topk(q.to(_dev()), qst_b200.CorpusIndex(c[:6].to(_dev())), 10)
+    want_val, want_idx = _oracle_topk(q, c[:6], 10)
+    assert_same_ranking(res.indices[:, :6], res.values[:, :6], want_idx, want_val, "N<k")
+    assert bool((res.indices[:, 6:] == -1).all()) and bool(torch.isinf(res.values[:, 6:]).all())
+
+
+def test_topk_clustered_near_ties_uses_certificate():
+    """corpus = centroid + 0.3*noise: near-ties much denser than the bf16 error -> the certificate
+    must flag and the exact re-scan must restore the exact ranking."""
+    import qst_b200
+    q = qst_b200.synth.clustered_embeddings(64, 128, 5, n_centroids=8, noise=0.02)
+    c = qst_b200.synth.clustered_embeddings(20000, 128, 6, n_centroids=8, noise=0.02)
+    want_val, want_idx = _oracle_topk(q, c, 100)
+    index = qst_b200.CorpusIndex(c.to(_dev()))
+    raw = qst_b200.topk(q.to(_dev()), index, 100, exact=False)
+    res = qst_b200.topk(q.to(_dev()), index, 100, exact=True)
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, "clustered")
+    assert bool((res.margin > 0).all())
+    # informational: how many queries the first pass could not certify
+    print("uncertified after bf16 pass:", int((raw.margin <= 0).sum()), "of", raw.margin.numel())
+
+
+def test_exact_rescan_repairs_a_deliberately_starved_first_pass():
+    """kprime == k leaves no head-room: wherever the bf16 order differs from the fp32 order the
+    certificate must fire, and the re-scan must repair the list."""
+    import qst_b200
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(50, 256, generator=g)
+    c = torch.randn(50000, 256, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, 32)
+    index = qst_b200.CorpusIndex(c.to(_dev()))
+    res = qst_b200.topk(q.to(_dev()), index, 32, kprime=32, exact=True)
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, "starved")
+
+
+def test_chunk_merge_and_evaluator_metrics_bit_identical():
+    """BASELINE.json config 1 through the drop-in evaluator vs the oracle evaluator."""
+    import qst_b200
+    from oracle import ir_oracle
+    for use_part in (True, False):
+        q, c, queries, corpus, relevant = qst_b200.synth.ir_eval_set(1000, 10000, 384, use_part_pos=use_part)
+        table = torch.cat([q, c])
+        kw = dict(corpus_chunk_size=3000, mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1, 3, 5, 10],
+                  precision_recall_at_k=[1, 3, 5, 10], map_at_k=[10], write_csv=False)
+        ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
+            "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score}, **kw)
+        ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, score_functions={
+            "cos_sim": ir_oracle.cos_sim, "dot_score": ir_oracle.dot_score}, **kw)
+        model = qst_b200.synth.TableModel(table.to(_dev()))
+        ranked = ev.rank(model)
+        ref_model = ir_oracle.PrecomputedEmbeddingModel(table)
+        hits = ref.collect_hits(ref_model)
+        identical = True
+        for fn in ("cos_sim", "dot_score"):
+            want_ids = ir_oracle.ranked_ids(hits[fn], 10)
+            got_rows = ranked[fn].indices.cpu().tolist()
+            got_ids = [[f"d{j}" for j in row] for row in got_rows]
+            if got_ids != want_ids:      # only legal difference: swaps of scores tied within 1e-6
+                identical = False
+                want_val, want_idx = _oracle_topk(q, c, 10, fn, chunk=3000)
+                if fn == "cos_sim":
+                    assert_same_ranking(ranked[fn].indices, ranked[fn].values, want_idx, want_val, fn)
+            # metrics are bit-identical GIVEN the ranking: feed our ranking to the reference loops
+            own_hits = [[{"corpus_id": f"d{j}", "score": float(-r)} for r, j in enumerate(row)] for row in got_rows]
+            want_m = ref.compute_metrics(own_hits)
+            got_m = ev.compute_metrics_from_ranking(ranked[fn].indices)
+            for metric in want_m:
+                for k, v in want_m[metric].items():
+                    assert float(got_m[metric][k]) == float(v), (fn, metric, k)
+        if identical:                    # then the whole evaluator call is bit-identical too
+            got = ev.compute_metrices(model)
+            want = ref.compute_metrices(ref_model)
+            for fn in want:
+                for metric in want[fn]:
+                    for k, v in want[fn][metric].items():
+                        assert float(got[fn][metric][k]) == float(v), (fn, metric, k)
+            assert ev(model) == ref(ref_model)
+        print("rankings identical to the oracle:", identical)
+
+
+def test_metrics_kernel_bit_identical_on_random_rankings():
+    """K4 alone: random rankings with hits, misses, relevant ids outside the corpus, k > list length."""
+    import qst_b200
+    from qst_b200 import metrics
+    from oracle import ir_oracle
+    rng = np.random.default_rng(14)
+    n_q, n_c, K = 257, 500, 100
+    queries = {f"q{i}": str(i) for i in range(n_q)}
+    corpus = {f"d{i}": str(i) for i in range(n_c)}
+    relevant = {}
+    for i in range(n_q):
+        rel = {f"d{j}" for j in rng.choice(n_c, size=rng.integers(1, 12), replace=False)}
+        if i % 7 == 0:
+            rel.add("not-in-corpus")            # counts in the denominators, can never be hit
+        relevant[f"q{i}"] = rel
+    k_lists = dict(mrr_at_k=[5, 10, 200], ndcg_at_k=[5, 10, 100, 200], accuracy_at_k=[1, 3, 5, 10],
+                   precision_recall_at_k=[1, 3, 5, 10, 100, 200], map_at_k=[1, 10, 100, 200])
+    ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, write_csv=False,
+                                                        score_functions={"cos_sim": ir_oracle.cos_sim}, **k_lists)
+    ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, write_csv=False,
+                                                score_functions={"cos_sim": qst_b200.cos_sim}, **k_lists)
+    ranked = np.stack([rng.permutation(n_c)[:K] for _ in range(n_q)])
+    hits = [[{"corpus_id": f"d{j}", "score": float(K - r)} for r, j in enumerate(row)] for row in ranked]
+    want = ref.compute_metrics(hits)
+    got = ev.compute_metrics_from_ranking(torch.from_numpy(ranked).to(_dev()))
+    for metric in want:
+        for k, v in want[metric].items():
+            assert float(got[metric][k]) == float(v), (metric, k, got[metric][k], v)
+
+
+def test_merge_kernel_against_sort():
+    from qst_b200 import sharded
+    g = torch.Generator().manual_seed(1)
+    G, Q, k = 5, 300, 37
+    vals = torch.randn(G, Q, k, generator=g)
+    vals[2, :, 5:9] = vals[3, :, 5:9]                       # cross-list score ties -> lower id first
+    vals = vals.sort(dim=2, descending=True).values
+    idx = torch.stack([torch.randperm(100000, generator=g)[:Q * k].view(Q, k) + 100000 * s for s in range(G)])
+    idx[4, :, 30:] = -1                                      # a short list (shard smaller than k)
+    vals[4, :, 30:] = float("-inf")
+    mv, mi = sharded.merge_topk(vals.to(_dev()), idx.to(_dev()))
+    flat_v = vals.permute(1, 0, 2).reshape(Q, G * k)
+    flat_i = idx.permute(1, 0, 2).reshape(Q, G * k)
+    key_i = torch.where(flat_i < 0, torch.full_like(flat_i, 2 ** 62), flat_i)
+    order = torch.argsort(key_i, dim=1, stable=True)
+    flat_v, flat_i = flat_v.gather(1, order), flat_i.gather(1, order)
+    order = torch.argsort(flat_v, dim=1, descending=True, stable=True)[:, :k]
+    assert torch.equal(mv.cpu(), flat_v.gather(1, order))
+    assert torch.equal(mi.cpu(), flat_i.gather(1, order))
+
+
+def test_single_process_shard_emulation_matches_global():
+    """G shards on one GPU, merged on device == the unsharded answer."""
+    import qst_b200
+    from qst_b200 import sharded
+    g = torch.Generator().manual_seed(2)
+    q = torch.randn(70, 128, generator=g)
+    c = torch.randn(10007, 128, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, 50)
+    parts_v, parts_i = [], []
+    for r in range(4):
+        s, e = sharded.shard_bounds(c.shape[0], 4, r)
+        res = qst_b200.topk(q.to(_dev()), qst_b200.CorpusIndex(c[s:e].to(_dev()), idx_offset=s), 50)
+        parts_v.append(res.values)
+        parts_i.append(res.indices)
+    mv, mi = sharded.merge_topk(torch.stack(parts_v), torch.stack(parts_i))
+    assert_same_ranking(mi, mv, want_idx, want_val, "sharded")
+
+
+def test_host_buffer_entry_and_dense_callable():
+    import qst_b200
+    from oracle import ir_oracle
+    g = torch.Generator().manual_seed(4)
+    q = torch.randn(33, 96, generator=g)
+    c = torch.randn(500, 96, generator=g)
+    index = qst_b200.CorpusIndex(c.to(_dev()))
+    vals, idx = qst_b200.topk_host(q.pin_memory(), index, 10)
+    want_val, want_idx = _oracle_topk(q, c, 10)
+    assert not vals.is_cuda and vals.is_pinned()
+    assert_same_ranking(idx, vals, want_idx, want_val, "host entry")
+    dense = qst_b200.cos_sim(q.to(_dev()), c.to(_dev()))
+    torch.testing.assert_close(dense.cpu(), ir_oracle.cos_sim(q, c), rtol=0, atol=2e-6)
+    with pytest.raises(qst_b200.QstError):
+        qst_b200.topk(q, index, 10)            # CPU queries: no fallback
