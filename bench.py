@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the retrieval-scoring hot path (BASELINE.json metric: queries/sec on a 1M x 768
+corpus, top-100), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic queries: K1 on the queries,
+K2 tensor-core scoring + streaming top-k', K3 fp32 rescoring/ordering (+ the exact re-scan kernels,
+which find nothing to do when every query is certified) and, for N > 1, the NCCL all-gather of the
+per-shard lists and the on-device merge.
+
+Workload (config 3 of BASELINE.json): 10 000 queries x 1 000 000 corpus rows x 768-d, fp32 masters
+-> bf16 tensor-core operands, k = 100.  For N > 1 the 1M-row corpus is sharded over the N GPUs
+ and the query batch grows to N x 10 000, so the per-GPU work is fixed
+(weak scaling) and `value` is all queries of all ranks / max-over-ranks device time.
+
+  value      inputs resident in HBM, CUDA-event time on the launching stream
+  e2e        the same step through the host-buffer entry (`qst_b200.topk_host`): pinned host
+             queries are copied in and the ranking is copied back inside the timed region
+  roofline   dominant kernel (score_select_kernel): 2*Q*N*D FLOP per launch / its mean duration
+             inside the steps, against the measured sustained bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (restated sentence-transformers 2.2.2 path: cos_sim -> per-chunk
+             torch.topk -> .tolist() -> per-hit dict lists -> sorted) on a bounded slice of the same
+             workload, all host threads, scaled by the corpus ratio
+`--impl reference` times only that CPU path and prints it in the same format.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q_PER_GPU = 10_000
+N_CORPUS = 1_000_000
+DIM = 768
+TOPK = 100
+CPU_SAMPLE_Q = 1000
+CPU_SAMPLE_N = 100_000
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle) -- the only place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int):
+    """Times the restated reference CPU path on a Q=1000 x N=100k x 768 slice (two 50k corpus
+    chunks, as corpus_chunk_size=50000 of ir_evauation_script.py:161 would cut it)."""
+    import torch
+    from oracle import ir_oracle
+    import qst_b200  # synthetic generators only (no GPU work here)
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    q = qst_b200.synth.gaussian_embeddings(CPU_SAMPLE_Q, DIM, 20)
+    c = qst_b200.synth.gaussian_embeddings(CPU_SAMPLE_N, DIM, 21)
+    table = torch.cat([q, c])
+    queries = {str(i): str(i) for i in range(CPU_SAMPLE_Q)}
+    corpus = {str(i): str(CPU_SAMPLE_Q + i) for i in range(CPU_SAMPLE_N)}
+    relevant = {str(i): {str(i)} for i in range(CPU_SAMPLE_Q)}
+    ev = ir_oracle.InformationRetrievalEvaluatorOracle(
+        queries, corpus, relevant, corpus_chunk_size=50000, mrr_at_k=[10], ndcg_at_k=[10],
+        accuracy_at_k=[1], precision_recall_at_k=[1], map_at_k=[TOPK],
+        score_functions={"cos_sim": ir_oracle.cos_sim}, write_csv=False)
+    model = ir_oracle.PrecomputedEmbeddingModel(table)
+
+    def one():
+        hits = ev.collect_hits(model)                    # cos_sim -> topk -> tolist -> dict lists
+        return ir_oracle.ranked_ids(hits["cos_sim"], TOPK)  # per-query stable sort
+
+    for _ in range(max(warmup, 1)):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    # scale the slice to the full corpus: work is linear in N (same number of queries per second
+    # on N rows costs N/N_sample times as long)
+    qps_full = CPU_SAMPLE_Q / (dt * (N_CORPUS / CPU_SAMPLE_N))
+    return {"value": qps_full, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"Q={CPU_SAMPLE_Q} x N={CPU_SAMPLE_N} x D={DIM}, k={TOPK}, 2 chunks of 50000; "
+                      f"{dt * 1e3:.0f} ms/step measured, scaled x{N_CORPUS // CPU_SAMPLE_N} in corpus size "
+                      f"(extrapolated)", "ms_per_sample_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    base = cpu_reference_run(steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "queries/sec, 1Mx768 corpus top-100", "value": base["value"],
+        "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": base["ms_per_sample_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cos_sim + top-{TOPK}: {Q_PER_GPU} queries x {N_CORPUS} corpus x {DIM}-d "
+                               f"(CPU path timed on a bounded slice, see cpu_baseline.sample)"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import qst_b200
+    from qst_b200 import scoring, sharded, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic inputs (seed 14 family; generated on the device in slabs: 3 GB of fp32) ----
+    Q = Q_PER_GPU * world
+    n0, n1 = sharded.shard_bounds(N_CORPUS, world, rank)
+    gen = torch.Generator(device=dev).manual_seed(14 + 100)
+    corpus_full_rows = []
+    # every rank draws the same global corpus stream and keeps its own rows, so the union over
+    # ranks is the same 1M-row corpus whatever N is
+    slab = 125_000
+    for s in range(0, N_CORPUS, slab):
+        x = torch.randn(slab, DIM, generator=gen, device=dev, dtype=torch.float32)
+        lo, hi = max(s, n0), min(s + slab, n1)
+        if lo < hi:
+            corpus_full_rows.append(x[lo - s:hi - s].clone())
+        del x
+    shard = torch.cat(corpus_full_rows)
+    del corpus_full_rows
+    qgen = torch.Generator(device=dev).manual_seed(14 + 200)
+    queries = torch.randn(Q, DIM, generator=qgen, device=dev, dtype=torch.float32)
+    queries_host = queries.cpu().pin_memory()
+
+    if world > 1:
+        corp = sharded.ShardedCorpus(shard, N_CORPUS, "cos_sim", query_tile=Q_PER_GPU * 2)
+        index = corp.index
+    else:
+        corp = None
+        index = qst_b200.CorpusIndex(shard, "cos_sim", idx_offset=0)
+    del shard
+    torch.cuda.synchronize()
+
+    def step_device():
+        if corp is not None:
+            return corp.topk(queries, TOPK)
+        r = scoring.topk(queries, index, TOPK)
+        return r.values, r.indices, r.margin
+
+    def step_host():
+        if corp is not None:
+            qd = queries_host.to(dev, non_blocking=True)
+            v, i, _ = corp.topk(qd, TOPK)
+            vh = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            ih = torch.empty(i.shape, dtype=i.dtype, pin_memory=True)
+            vh.copy_(v, non_blocking=True)
+            ih.copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return vh, ih
+        return scoring.topk_host(queries_host, index, TOPK)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / n, out
+
+    for _ in range(warmup):
+        out = step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_step, out = timed(step_device, steps)
+    clocks = sampler.stop()
+    margin = out[2]
+    uncertified = int((margin <= 0).sum())
+
+    # ---- the dominant kernel alone, on the same stream, inside the same kind of step -----------
+    plan = scoring.make_plan(Q, index.n, DIM, TOPK, 0, "cos_sim")
+    pq = scoring.prepare_rows(queries, True)
+    ws = scoring._workspace(plan.ws_bytes, dev, "select")
+    lib = _lib.load()
+    st = _lib.stream_ptr(dev)
+    k2_ms = []
+    for i in range(warmup + steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_device()                                   # keep the device in the steady state of a step
+        a.record()
+        _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), index.rows.bf16.data_ptr(),
+                                        ws.data_ptr(), st))
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            k2_ms.append(a.elapsed_time(b))
+    k2 = sum(k2_ms) / len(k2_ms)
+
+    # ---- end to end through the host-buffer entry --------------------------------------------
+    for _ in range(2):
+        step_host()
+    ms_e2e, _ = timed(step_host, steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    flop = 2.0 * Q * index.n * DIM
+    achieved = flop / (k2 * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "score_select_ncu_summary.json")
+    if os.path.isfile(prof):
+        try:
+            with open(prof) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu = cpu_reference_run(5, 1) if world == 1 and not args.no_cpu_baseline else None
+    h2d = Q * DIM * 4
+    d2h = Q * TOPK * (4 + 8)
+    line = {
+        "metric": "queries/sec, 1Mx768 corpus top-100",
+        "value": Q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"cos_sim + top-{TOPK}: {Q} queries x {N_CORPUS} corpus x {DIM}-d, fp32 masters, "
+                               f"bf16 tensor-core first pass k'={plan.kprime}, fp32 rescore; corpus sharded over "
+                               f"{world} GPU(s), {Q_PER_GPU} queries per GPU per step",
+                   "l2": "inputs larger than L2 (bf16 corpus shard %.2f GB + fp32 masters)" % (index.n * DIM * 2 / 1e9),
+                   "plan": {"m_tiles": plan.m_tiles, "n_tiles": plan.n_tiles, "stripes": plan.stripes,
+                            "units": plan.units, "grid": plan.grid},
+                   "uncertified_queries_after_first_pass_and_rescan": uncertified},
+        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+        "gpu_launches": steps * (6 + (1 if world > 1 else 0)),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "score_select_kernel",
+                     "kernel_ms": k2, "peak_source": peaks["_source"] + " sustained bf16 (kernel timed inside the step loop)",
+                     "frac_of_burst_peak": achieved / float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))},
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,30 @@ __device__ void block_bitonic_sort(float* sc, int32_t* ix, int n2) {
   __syncthreads();
 }
 
+// Exact fp32 dot product of a shared-memory query row with a global corpus row, one warp.
+// Both K3 (rescoring) and the exact re-scan call this, so a row gets bit-identical scores in both.
+__device__ __forceinline__ float warp_dot_f32(const float* __restrict__ qrow, const float* __restrict__ crow, int D,
+                                              bool vec4, int lane) {
+  float acc = 0.f;
+  if (vec4) {
+    const float4* c4 = reinterpret_cast<const float4*>(crow);
+    const float4* q4 = reinterpret_cast<const float4*>(qrow);
+    for (int i = lane; i < D / 4; i += 32) {
+      const float4 c = __ldg(c4 + i);
+      const float4 a = q4[i];
+      acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc);
+      acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) acc = fmaf(qrow[i], __ldg(crow + i), acc);
+  }
+  return warp_sum(acc);
+}
+
+__device__ __forceinline__ float apply_score(float dot, int score, float q_inv, const float* c_inv, int row) {
+  return score == QST_SCORE_COS ? (dot * q_inv) * (c_inv ? c_inv[row] : 1.0f) : dot;
+}
+
 struct FinParams {
   int Q, N, D;
   int k, kprime, cap, m_tiles, stripes, score;
@@ -195,26 +219,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   const bool vec4 = (P.D % 4) == 0 && ((reinterpret_cast<uintptr_t>(P.c_f32) & 15u) == 0);
   for (int j = warp; j < ncand; j += kFinWarps) {
     const int ci = idx[j];
-    const float* crow = P.c_f32 + (size_t)ci * P.D;
-    float acc = 0.f;
-    if (vec4) {
-      const float4* c4 = reinterpret_cast<const float4*>(crow);
-      const float4* q4 = reinterpret_cast<const float4*>(qrow);
-      for (int i = lane; i < P.D / 4; i += 32) {
-        const float4 c = __ldg(c4 + i);
-        const float4 a = q4[i];
-        acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc);
-        acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
-      }
-    } else {
-      for (int i = lane; i < P.D; i += 32) acc = fmaf(qrow[i], __ldg(crow + i), acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float sc = acc;
-      if (P.score == QST_SCORE_COS) sc = (acc * qi) * (P.c_inv ? P.c_inv[ci] : 1.0f);
-      exact[j] = sc;
-    }
+    const float acc = warp_dot_f32(qrow, P.c_f32 + (size_t)ci * P.D, P.D, vec4, lane);
+    if (lane == 0) exact[j] = apply_score(acc, P.score, qi, P.c_inv, ci);
   }
   // pad to a power of two for the sort
   int n2 = 1;
@@ -328,14 +334,11 @@ __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k
     __syncthreads();
     const float thr = cur_val[(size_t)q * k + (k - 1)];  // exact k-th best among the candidates
     const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
+    const bool vec4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(c_f32) & 15u) == 0);
     for (int row = blockIdx.x * 8 + warp; row < N; row += gridDim.x * 8) {
-      const float* crow = c_f32 + (size_t)row * D;
-      float acc = 0.f;
-      for (int i = lane; i < D; i += 32) acc = fmaf(s_q[i], __ldg(crow + i), acc);
-      acc = warp_sum(acc);
+      const float acc = warp_dot_f32(s_q, c_f32 + (size_t)row * D, D, vec4, lane);
       if (lane == 0) {
-        float sc = acc;
-        if (score == QST_SCORE_COS) sc = (acc * qi) * (c_inv ? c_inv[row] : 1.0f);
+        const float sc = apply_score(acc, score, qi, c_inv, row);
         if (sc >= thr) {
           const int p = atomicAdd(&counts[q], 1);
           if (p < kRescanCap) { coll_val[(size_t)f * kRescanCap + p] = sc; coll_idx[(size_t)f * kRescanCap + p] = row; }

@@ -333,10 +333,7 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
   QST_CHECK_ARG(dtype == QST_F32 || dtype == QST_F16 || dtype == QST_BF16, "quadruplet: bad dtype %d", dtype);
   QST_CHECK_ARG(a.reduction >= QST_RED_NONE && a.reduction <= QST_RED_MEAN, "quadruplet: bad reduction %d", a.reduction);
   QST_CHECK_ARG(a.prm.p > 0.f, "p must be positive, %g given", (double)a.prm.p);
-  QST_CHECK_ARG(a.a && a.po && a.pa && a.ne, "quadruplet: null input pointer");
-  if (kind != K_BWD) QST_CHECK_ARG(a.loss_out != nullptr, "quadruplet: null loss_out");
-  if (kind != K_BWD && a.reduction != QST_RED_NONE) QST_CHECK_ARG(a.ws != nullptr, "quadruplet: null workspace");
-  if (kind == K_BWD) QST_CHECK_ARG(a.saved && a.grad_out, "quadruplet bwd: null saved/grad_out");
+  if (kind != K_BWD) QST_CHECK_ARG(a.loss_out != nullptr || (a.B == 0 && a.reduction == QST_RED_NONE), "quadruplet: null loss_out");
   if (a.B == 0) {
     if (kind != K_BWD && a.reduction != QST_RED_NONE) {
       // sum over nothing = 0, mean over nothing = nan (torch semantics)
@@ -345,6 +342,9 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
     }
     return QST_OK;
   }
+  QST_CHECK_ARG(a.a && a.po && a.pa && a.ne, "quadruplet: null input pointer");
+  if (kind != K_BWD && a.reduction != QST_RED_NONE) QST_CHECK_ARG(a.ws != nullptr, "quadruplet: null workspace");
+  if (kind == K_BWD) QST_CHECK_ARG(a.saved && a.grad_out, "quadruplet bwd: null saved/grad_out");
   const int pm = a.prm.p == 2.0f ? PM_2 : (a.prm.p == 1.0f ? PM_1 : (isinf(a.prm.p) ? PM_INF : PM_GEN));
   const size_t esz = dtype == QST_F32 ? 4 : 2;
   const int vec = (int)(16 / esz);
