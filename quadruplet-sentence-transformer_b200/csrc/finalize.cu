@@ -319,29 +319,74 @@ __global__ void rescan_list_kernel(const float* margin, int Q, int* flagged, Res
   for (int i = threadIdx.x; i < Q; i += blockDim.x) counts[i] = 0;
 }
 
+constexpr int kRescanBatch = 16;   // flagged queries scored per corpus pass (register accumulators)
+
+// One corpus pass per batch of kRescanBatch flagged queries: the batch's query rows sit in shared
+// memory, every warp streams corpus rows (each row read once per batch) and keeps one accumulator
+// per query.  The per-query operation order is exactly warp_dot_f32's, so scores are bit-identical
+// to the ones K3 produced for the same (query, row).
 __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k, int score, const float* __restrict__ q_f32,
                                                              const float* __restrict__ q_inv, const float* __restrict__ c_f32,
                                                              const float* __restrict__ c_inv, const float* __restrict__ cur_val,
                                                              const int* __restrict__ flagged, const RescanScratch* hdr,
                                                              int* counts, float* coll_val, int* coll_idx) {
-  extern __shared__ float s_q[];  // one query row
+  extern __shared__ float s_q[];  // [kRescanBatch][D]
+  __shared__ float s_thr[kRescanBatch], s_qi[kRescanBatch];
+  __shared__ int s_qid[kRescanBatch];
   const int nf = hdr->n_flagged;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int f = blockIdx.y; f < nf; f += gridDim.y) {
-    const int q = flagged[f];
+  const bool vec4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(c_f32) & 15u) == 0);
+  for (int f0 = 0; f0 < nf; f0 += kRescanBatch) {
+    const int nb = min(kRescanBatch, nf - f0);
     __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) s_q[i] = q_f32[(size_t)q * D + i];
+    for (int i = threadIdx.x; i < kRescanBatch * D; i += blockDim.x) {
+      const int b = i / D, j = i - b * D;
+      s_q[i] = b < nb ? q_f32[(size_t)flagged[f0 + b] * D + j] : 0.f;
+    }
+    if (threadIdx.x < kRescanBatch) {
+      const int b = threadIdx.x;
+      const int q = b < nb ? flagged[f0 + b] : 0;
+      s_qid[b] = q;
+      s_thr[b] = b < nb ? cur_val[(size_t)q * k + (k - 1)] : INFINITY;  // exact k-th best so far
+      s_qi[b] = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
+    }
     __syncthreads();
-    const float thr = cur_val[(size_t)q * k + (k - 1)];  // exact k-th best among the candidates
-    const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
-    const bool vec4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(c_f32) & 15u) == 0);
     for (int row = blockIdx.x * 8 + warp; row < N; row += gridDim.x * 8) {
-      const float acc = warp_dot_f32(s_q, c_f32 + (size_t)row * D, D, vec4, lane);
-      if (lane == 0) {
-        const float sc = apply_score(acc, score, qi, c_inv, row);
-        if (sc >= thr) {
-          const int p = atomicAdd(&counts[q], 1);
-          if (p < kRescanCap) { coll_val[(size_t)f * kRescanCap + p] = sc; coll_idx[(size_t)f * kRescanCap + p] = row; }
+      const float* crow = c_f32 + (size_t)row * D;
+      float acc[kRescanBatch];
+#pragma unroll
+      for (int b = 0; b < kRescanBatch; ++b) acc[b] = 0.f;
+      if (vec4) {
+        const float4* c4 = reinterpret_cast<const float4*>(crow);
+        for (int i = lane; i < D / 4; i += 32) {
+          const float4 c = __ldg(c4 + i);
+#pragma unroll
+          for (int b = 0; b < kRescanBatch; ++b) {
+            const float4 a = reinterpret_cast<const float4*>(s_q + (size_t)b * D)[i];
+            acc[b] = fmaf(a.x, c.x, acc[b]); acc[b] = fmaf(a.y, c.y, acc[b]);
+            acc[b] = fmaf(a.z, c.z, acc[b]); acc[b] = fmaf(a.w, c.w, acc[b]);
+          }
+        }
+      } else {
+        for (int i = lane; i < D; i += 32) {
+          const float c = __ldg(crow + i);
+#pragma unroll
+          for (int b = 0; b < kRescanBatch; ++b) acc[b] = fmaf(s_q[(size_t)b * D + i], c, acc[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kRescanBatch; ++b) {
+        const float dot = warp_sum(acc[b]);
+        if (lane == 0 && b < nb) {
+          const float sc = apply_score(dot, score, s_qi[b], c_inv, row);
+          if (sc >= s_thr[b]) {
+            const int q = s_qid[b];
+            const int p = atomicAdd(&counts[q], 1);
+            if (p < kRescanCap) {
+              coll_val[(size_t)(f0 + b) * kRescanCap + p] = sc;
+              coll_idx[(size_t)(f0 + b) * kRescanCap + p] = row;
+            }
+          }
         }
       }
     }
@@ -432,7 +477,7 @@ extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int scor
                                 qst_stream_t stream) {
   QST_CHECK_ARG(q_f32 && c_f32 && out_val && out_idx && margin_inout && scratch, "exact_rescan: null argument");
   QST_CHECK_ARG(score == QST_SCORE_COS || score == QST_SCORE_DOT, "exact_rescan: unsupported score %d", score);
-  QST_CHECK_ARG(D * 4 <= 160 * 1024, "exact_rescan: D too large");
+  QST_CHECK_ARG((size_t)kRescanBatch * D * 4 <= 200 * 1024, "exact_rescan: D too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
   RescanScratch* hdr = reinterpret_cast<RescanScratch*>(p); p += 256;
@@ -442,11 +487,13 @@ extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int scor
   int* coll_idx = reinterpret_cast<int*>(p);
   rescan_list_kernel<<<1, 1024, 0, st>>>(margin_inout, (int)Q, flagged, hdr, counts);
   QST_LAUNCH_CHECK();
-  const size_t smem = (size_t)D * 4;
+  const size_t smem = (size_t)kRescanBatch * D * 4;
   QST_CUDA(cudaFuncSetAttribute(rescan_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // grid.y strides over the flagged list on the device; its size is only an upper bound on
-  // useful parallelism, so no host read of n_flagged is needed
-  dim3 grid(148, (unsigned)(Q < 32 ? Q : 32));
+  // the flagged list is consumed on the device (no host read of n_flagged): with nothing flagged
+  // every CTA returns at once
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = sms * 2;
   rescan_collect_kernel<<<grid, 256, smem, st>>>((int)N, (int)D, k, score, q_f32, q_inv, c_f32, c_inv, out_val, flagged,
                                                  hdr, counts, coll_val, coll_idx);
   QST_LAUNCH_CHECK();

@@ -384,8 +384,8 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   if (sm_count <= 0) sm_count = 148;
   if (kprime <= 0) {
     // head-room so that the bf16 ordering error cannot push a true top-k document out of the
-    // candidate set (DESIGN.md "certificate"): k + max(k/2, 32), in steps of 32
-    int extra = k / 2 > 32 ? k / 2 : 32;
+    // candidate set (DESIGN.md "certificate"): k + max(3k/4, 32), in steps of 32
+    int extra = (3 * k) / 4 > 32 ? (3 * k) / 4 : 32;
     kprime = (int)round_up(k + extra, 32);
   }
   kprime = (int)round_up(kprime, 32);
