@@ -143,7 +143,8 @@ typedef struct qst_topk_plan {
   int64_t Q, N, D, D_pad;
   int32_t k, kprime, cap;        /* cap = per-row candidate capacity of one work unit */
   int32_t m_tiles, n_tiles, stripes, tiles_per_stripe, units;
-  int32_t grid, score;
+  int32_t grid, score;           /* grid = CTA groups launched (x ctas CTAs each) */
+  int32_t ctas, rows_per_unit;   /* CTAs per tile (2 = cta_group::2 pairs), query rows per work unit */
   size_t ws_bytes;
   size_t off_thr, off_cnt, off_cand; /* layout inside the workspace */
 } qst_topk_plan;

@@ -40,6 +40,7 @@ class TopkPlan(C.Structure):
                 ("m_tiles", C.c_int32), ("n_tiles", C.c_int32), ("stripes", C.c_int32),
                 ("tiles_per_stripe", C.c_int32), ("units", C.c_int32),
                 ("grid", C.c_int32), ("score", C.c_int32),
+                ("ctas", C.c_int32), ("rows_per_unit", C.c_int32),
                 ("ws_bytes", C.c_size_t), ("off_thr", C.c_size_t), ("off_cnt", C.c_size_t),
                 ("off_cand", C.c_size_t)]
 

@@ -12,7 +12,6 @@ namespace qst {
 
 constexpr int kFinThreads = 256;
 constexpr int kFinWarps = kFinThreads / 32;
-constexpr int BM_ = 128;  // must match score_select.cu
 
 // ------------------------------------------------------------------------------------------
 // CTA-wide: keep the k largest keys of (keys, idx)[0..n) -> compacted to the front (order
@@ -129,7 +128,7 @@ __device__ __forceinline__ float apply_score(float dot, int score, float q_inv, 
 
 struct FinParams {
   int Q, N, D;
-  int k, kprime, cap, m_tiles, stripes, score;
+  int k, kprime, cap, m_tiles, stripes, score, rows_per_unit;
   int sm_cap;  // smem candidate capacity (entries)
   const uint32_t* thr_hint;
   const int* unit_cnt;
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m = q / BM_, r = q % BM_;
+  const int m = q / P.rows_per_unit, r = q % P.rows_per_unit;
 
   // stage the fp32 query row and its squared norm
   float qq = 0.f;
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   uint32_t T = 0;
   int fill = 0;
   for (int s = 0; s < P.stripes; ++s) {
-    const size_t urow = (size_t)(s * P.m_tiles + m) * BM_ + r;
+    const size_t urow = (size_t)(s * P.m_tiles + m) * P.rows_per_unit + r;
     const int cnt = P.unit_cnt[urow];
     if (fill + cnt > P.sm_cap) {
       T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
@@ -439,6 +438,7 @@ extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspac
   P.Q = (int)plan->Q; P.N = (int)plan->N; P.D = (int)plan->D;
   P.k = plan->k; P.kprime = plan->kprime; P.cap = plan->cap;
   P.m_tiles = plan->m_tiles; P.stripes = plan->stripes; P.score = plan->score;
+  P.rows_per_unit = plan->rows_per_unit;
   int sm_cap = plan->kprime + plan->cap;
   if (sm_cap < 4096) sm_cap = 4096;
   P.sm_cap = sm_cap;

@@ -7,12 +7,18 @@
 //     pair_scores = score_function(query_embeddings, sub_corpus_embeddings)   # torch.mm
 //     torch.topk(pair_scores, min(max_k, chunk), dim=1, largest=True, sorted=False)
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
-//   warp 0      TMA producer: 128x64 query tile + 256x64 corpus tile per k-block into a
-//               4-stage 128B-swizzled smem ring (mbarrier full/empty pipeline)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) x4 per k-block,
-//               accumulating in TMEM; two 256-column accumulators are double-buffered so the
-//               epilogue of tile t overlaps the MMAs of tile t+1
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised).  Default: CTA PAIRS
+// (cta_group::2, cluster of 2): the pair computes a 256-query x 256-corpus-row tile, each CTA
+// stages its own 128 query rows and HALF of the corpus tile, which cuts the L2->smem traffic per
+// FLOP by 1.5x against the single-CTA tile and leaves room for a 6-stage ring.
+//   warp 0      TMA producer: 128x64 query tile + 128x64 (pair) / 256x64 (single) corpus tile per
+//               k-block into a 128B-swizzled smem ring (mbarrier full/empty pipeline); in pair
+//               mode both CTAs signal the LEADER's full barrier
+//   warp 1      MMA issuer (leader CTA only in pair mode): one thread issues tcgen05.mma
+//               (M=256|128, N=256, K=16) x4 per k-block, accumulating in TMEM; two 256-column
+//               accumulators are double-buffered so the epilogue of tile t overlaps the MMAs of
+//               tile t+1; tcgen05.commit (multicast to both CTAs) frees smem slots and publishes
+//               accumulators
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: thread r of the CTA owns query row r of the tile (TMEM lane r);
 //               tcgen05.ld 32 columns at a time, reject against the row's running threshold
@@ -26,6 +32,7 @@
 // query row through a global hint array (atomicMax), which removes the cold start of later units.
 #include "qst_common.cuh"
 #include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace qst {
 
@@ -33,21 +40,28 @@ constexpr int BM = 128;          // query rows per tile  (UMMA M)
 constexpr int BN = 256;          // corpus rows per tile (UMMA N)
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int kScoreThreads = 256;
 constexpr uint32_t A_BYTES = BM * BK * 2;
-constexpr uint32_t B_BYTES = BN * BK * 2;
-constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t TMEM_COLS = 512;  // 2 accumulators x 256 fp32 columns
-constexpr size_t kScoreSmemBytes = (size_t)STAGES * STAGE_BYTES + 1024;  // + alignment slack
+constexpr int MAX_STAGES = 6;
+
+template <int CTAS>
+struct Cfg {
+  static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int B_ROWS = BN / CTAS;                 // corpus rows staged by one CTA per tile
+  static constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
+  static constexpr int UNIT_ROWS = BM * CTAS;              // query rows of one work unit
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;  // + alignment slack
+};
 
 struct ScoreParams {
   int Q, N, num_kb;
   int m_tiles, n_tiles, stripes, tiles_per_stripe, units;
   int kprime, cap;
-  uint32_t* thr_hint;  // [m_tiles*BM] ordered keys, 0 = no threshold yet
-  int* unit_cnt;       // [units*BM]
-  uint2* unit_cand;    // [units*BM*cap]  (key, corpus row)
+  uint32_t* thr_hint;  // [m_tiles*UNIT_ROWS] ordered keys, 0 = no threshold yet
+  int* unit_cnt;       // [units*UNIT_ROWS]
+  uint2* unit_cand;    // [units*UNIT_ROWS*cap]  (key, corpus row)
   float* dense_out;    // dense mode only: [Q, N]
 };
 
@@ -122,13 +136,16 @@ __device__ __forceinline__ uint32_t warp_select_compact(uint2* __restrict__ buf,
   return T;
 }
 
-template <bool DENSE>
+template <int CTAS, bool DENSE>
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                     const ScoreParams P) {
+  using C = Cfg<CTAS>;
+  constexpr int STAGES = C::STAGES;
+  constexpr uint32_t STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[STAGES];
-  __shared__ __align__(8) uint64_t s_empty[STAGES];
+  __shared__ __align__(8) uint64_t s_full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t s_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t s_tmem_full[2];
   __shared__ __align__(8) uint64_t s_tmem_empty[2];
   __shared__ uint32_t s_tmem_base;
@@ -136,6 +153,8 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;   // 0 = pair leader
+  const int group = blockIdx.x / CTAS, n_groups = gridDim.x / CTAS;
   // 128B swizzle needs 1024-byte aligned stage bases
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
 
@@ -150,42 +169,55 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(&s_tmem_full[a]), 1);
-      ptx::mbar_init(ptx::smem_u32(&s_tmem_empty[a]), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&s_tmem_empty[a]), 4 * CTAS);  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), TMEM_COLS);
+  if (warp == 2) {
+    if (CTAS == 2) ptx::tmem_alloc_pair(ptx::smem_u32(&s_tmem_base), TMEM_COLS);
+    else ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), TMEM_COLS);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
   if (warp == 0 && lane == 0) {
     // ============================== TMA producer ==============================
     uint32_t stage = 0, phase = 0;
-    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+    for (int u = group; u < P.units; u += n_groups) {
       const int s = u / P.m_tiles, m = u - s * P.m_tiles;
       const int t0 = s * P.tiles_per_stripe;
       const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
+      const int q_row = m * C::UNIT_ROWS + (int)rank * BM;
       for (int t = t0; t < t1; ++t) {
+        const int c_row = t * BN + (int)rank * C::B_ROWS;
         for (int kb = 0; kb < P.num_kb; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
           const uint32_t full = ptx::smem_u32(&s_full[stage]);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(full, STAGE_BYTES);
           // queries are re-read by every corpus tile (keep in L2); a corpus tile is re-read by the
           // other query tiles walking the same stripe (normal priority)
-          ptx::tma_load_2d(sa, &tmap_q, full, kb * BK, m * BM, ptx::kEvictLast);
-          ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full, kb * BK, t * BN, ptx::kEvictNormal);
+          if (CTAS == 1) {
+            ptx::mbar_arrive_expect_tx(full, STAGE_BYTES);
+            ptx::tma_load_2d(sa, &tmap_q, full, kb * BK, q_row, ptx::kEvictLast);
+            ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full, kb * BK, c_row, ptx::kEvictNormal);
+          } else {
+            // both CTAs' bytes are accounted on the leader's barrier, which the MMA thread waits on
+            if (rank == 0) ptx::mbar_arrive_expect_tx(full, STAGE_BYTES * 2);
+            const uint32_t leader_full = ptx::mapa_shared(full, 0);
+            ptx::tma_load_2d_pair(sa, &tmap_q, leader_full, kb * BK, q_row, ptx::kEvictLast);
+            ptx::tma_load_2d_pair(sa + A_BYTES, &tmap_c, leader_full, kb * BK, c_row, ptx::kEvictNormal);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && lane == 0 && rank == 0) {
     // ============================== MMA issuer ================================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CTAS, BN);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+    for (int u = group; u < P.units; u += n_groups) {
       const int s = u / P.m_tiles;
       const int t0 = s * P.tiles_per_stripe;
       const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
@@ -202,12 +234,18 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the addr>>4 field
-            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+            else ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
           }
-          ptx::umma_commit(ptx::smem_u32(&s_empty[stage]));  // frees the smem slot when the MMAs retire
+          // frees the smem slot (in both CTAs) once the MMAs that read it have retired
+          if (CTAS == 2) ptx::umma_commit_pair(ptx::smem_u32(&s_empty[stage]), 3);
+          else ptx::umma_commit(ptx::smem_u32(&s_empty[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(ptx::smem_u32(&s_tmem_full[acc]));  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (CTAS == 2) ptx::umma_commit_pair(ptx::smem_u32(&s_tmem_full[acc]), 3);
+        else ptx::umma_commit(ptx::smem_u32(&s_tmem_full[acc]));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -215,18 +253,18 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   } else if (warp >= 4) {
     // ============================== epilogue ==================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
-    const int row_in_tile = quarter * 32 + lane;
+    const int row_in_unit = (int)rank * BM + quarter * 32 + lane;
     int* hist = s_hist[quarter];
     uint32_t acc = 0, acc_phase = 0;
-    for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+    for (int u = group; u < P.units; u += n_groups) {
       const int s = u / P.m_tiles, m = u - s * P.m_tiles;
       const int t0 = s * P.tiles_per_stripe;
       const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
-      const int grow = m * BM + row_in_tile;
+      const int grow = m * C::UNIT_ROWS + row_in_unit;
       const bool row_ok = grow < P.Q;
       float thr = row_ok ? -INFINITY : INFINITY;
       int cnt = 0;
-      uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * BM + row_in_tile) * (size_t)P.cap;
+      uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * C::UNIT_ROWS + row_in_unit) * (size_t)P.cap;
       for (int t = t0; t < t1; ++t) {
         if (!DENSE && row_ok) {  // pick up thresholds published by other units of this row
           const uint32_t hk = __ldcg(&P.thr_hint[grow]);
@@ -244,7 +282,10 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             // every column of this accumulator is now in registers: hand TMEM back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
+            if (lane == 0) {
+              if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
+              else ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
+            }
           }
           const int col0 = t * BN + chunk * 32;
           if (col0 + 32 > P.N) {  // ragged last tile: columns >= N were zero-filled by TMA
@@ -291,16 +332,17 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (!DENSE) P.unit_cnt[(size_t)u * BM + row_in_tile] = cnt;
+      if (!DENSE) P.unit_cnt[(size_t)u * C::UNIT_ROWS + row_in_unit] = cnt;
     }
   }
 
   // ------------------------------ teardown ------------------------------
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -340,25 +382,48 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t d
   return QST_OK;
 }
 
-static int launch_score(bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P, int64_t d_pad,
-                        int grid, cudaStream_t st) {
+template <int CTAS, bool DENSE>
+static int launch_score_t(const void* q_bf16, const void* c_bf16, const ScoreParams& P, int64_t d_pad, int groups,
+                          cudaStream_t st) {
+  using C = Cfg<CTAS>;
   CUtensorMap tq, tc;
   int rc = make_tmap(&tq, q_bf16, P.Q, d_pad, BM);
   if (rc) return rc;
-  rc = make_tmap(&tc, c_bf16, P.N, d_pad, BN);
+  rc = make_tmap(&tc, c_bf16, P.N, d_pad, C::B_ROWS);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    QST_CUDA(cudaFuncSetAttribute(score_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kScoreSmemBytes));
-    QST_CUDA(cudaFuncSetAttribute(score_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kScoreSmemBytes));
-    attr_done = true;
-  }
-  if (dense) score_select_kernel<true><<<grid, kScoreThreads, kScoreSmemBytes, st>>>(tq, tc, P);
-  else score_select_kernel<false><<<grid, kScoreThreads, kScoreSmemBytes, st>>>(tq, tc, P);
-  QST_LAUNCH_CHECK();
+  auto kern = score_select_kernel<CTAS, DENSE>;
+  QST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(groups * CTAS));
+  cfg.blockDim = dim3(kScoreThreads);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  QST_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tc, P));
   return QST_OK;
+}
+
+static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P,
+                        int64_t d_pad, int groups, cudaStream_t st) {
+  if (ctas == 2) {
+    return dense ? launch_score_t<2, true>(q_bf16, c_bf16, P, d_pad, groups, st)
+                 : launch_score_t<2, false>(q_bf16, c_bf16, P, d_pad, groups, st);
+  }
+  return dense ? launch_score_t<1, true>(q_bf16, c_bf16, P, d_pad, groups, st)
+               : launch_score_t<1, false>(q_bf16, c_bf16, P, d_pad, groups, st);
+}
+
+// QST_SCORE_CTAS=1 forces the single-CTA tile (debugging / comparison); default is CTA pairs.
+static int default_ctas() {
+  const char* e = getenv("QST_SCORE_CTAS");
+  if (e && e[0] == '1') return 1;
+  return 2;
 }
 
 static int device_sm_count() {
@@ -394,8 +459,11 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim(D);
   plan->k = k; plan->kprime = kprime; plan->cap = 2 * kprime;
   plan->score = score;
-  plan->m_tiles = (int)ceil_div(Q, BM);
+  plan->ctas = default_ctas();
+  plan->rows_per_unit = BM * plan->ctas;
+  plan->m_tiles = (int)ceil_div(Q, plan->rows_per_unit);
   plan->n_tiles = (int)ceil_div(N, BN);
+  const int groups_max = sm_count / plan->ctas > 0 ? sm_count / plan->ctas : 1;
   // stripes: minimise  waves * (tiles_per_stripe + cold-start cost)  over S
   const int r_min = 4;
   int s_max = plan->n_tiles / r_min;
@@ -407,18 +475,19 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
     const int R = (int)ceil_div(plan->n_tiles, S);
     const int S_eff = (int)ceil_div(plan->n_tiles, R);  // stripes actually non-empty
     const int64_t units = (int64_t)plan->m_tiles * S_eff;
-    const int64_t waves = ceil_div(units, sm_count);
+    const int64_t waves = ceil_div(units, groups_max);
     const double cost = (double)waves * ((double)R + 2.0);
     if (cost < best - 1e-9) { best = cost; best_s = S_eff; }
   }
   plan->tiles_per_stripe = (int)ceil_div(plan->n_tiles, best_s);
   plan->stripes = (int)ceil_div(plan->n_tiles, plan->tiles_per_stripe);
   plan->units = plan->m_tiles * plan->stripes;
-  plan->grid = plan->units < sm_count ? plan->units : sm_count;
+  plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
   size_t off = 0;
-  plan->off_thr = off;  off += round_up((size_t)plan->m_tiles * BM * sizeof(uint32_t), 256);
-  plan->off_cnt = off;  off += round_up((size_t)plan->units * BM * sizeof(int), 256);
-  plan->off_cand = off; off += (size_t)plan->units * BM * (size_t)plan->cap * sizeof(uint2);
+  const size_t ur = (size_t)plan->rows_per_unit;
+  plan->off_thr = off;  off += round_up((size_t)plan->m_tiles * ur * sizeof(uint32_t), 256);
+  plan->off_cnt = off;  off += round_up((size_t)plan->units * ur * sizeof(int), 256);
+  plan->off_cand = off; off += (size_t)plan->units * ur * (size_t)plan->cap * sizeof(uint2);
   plan->ws_bytes = off;
   return QST_OK;
 }
@@ -438,8 +507,9 @@ extern "C" int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, c
   P.thr_hint = reinterpret_cast<uint32_t*>(ws + plan->off_thr);
   P.unit_cnt = reinterpret_cast<int*>(ws + plan->off_cnt);
   P.unit_cand = reinterpret_cast<uint2*>(ws + plan->off_cand);
-  QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * BM * sizeof(uint32_t), st));
-  return launch_score(false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
+  QST_CHECK_ARG(plan->ctas == 1 || plan->ctas == 2, "score_select: plan->ctas must be 1 or 2");
+  QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * plan->rows_per_unit * sizeof(uint32_t), st));
+  return launch_score(plan->ctas, false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
 }
 
 extern "C" int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad, float* out,
@@ -448,11 +518,13 @@ extern "C" int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16
   QST_CHECK_ARG(Q >= 1 && N >= 1 && D_pad >= BK && D_pad % BK == 0, "score_dense: bad shape");
   ScoreParams P{};
   P.Q = (int)Q; P.N = (int)N; P.num_kb = (int)(D_pad / BK);
-  P.m_tiles = (int)ceil_div(Q, BM); P.n_tiles = (int)ceil_div(N, BN);
+  const int ctas = default_ctas();
+  P.m_tiles = (int)ceil_div(Q, BM * ctas); P.n_tiles = (int)ceil_div(N, BN);
   P.stripes = 1; P.tiles_per_stripe = P.n_tiles; P.units = P.m_tiles;
   P.dense_out = out;
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  const int grid = P.units < sms ? P.units : sms;
-  return launch_score(true, q_bf16, c_bf16, P, D_pad, grid, reinterpret_cast<cudaStream_t>(stream));
+  const int groups_max = sms / ctas;
+  const int groups = P.units < groups_max ? P.units : groups_max;
+  return launch_score(ctas, true, q_bf16, c_bf16, P, D_pad, groups, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -14,6 +14,13 @@ def _dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+def ctas(request, monkeypatch):
+    """Both tile shapes of K2: cta_group::2 pairs (default) and the single-CTA tile."""
+    monkeypatch.setenv("QST_SCORE_CTAS", str(request.param))
+    return request.param
+
+
 def assert_same_ranking(got_idx, got_val, want_idx, want_val, what=""):
     """Index-for-index equality, except inside groups of reference scores within TIE."""
     got_idx, got_val = got_idx.cpu(), got_val.cpu()
@@ -39,7 +46,7 @@ def assert_same_ranking(got_idx, got_val, want_idx, want_val, what=""):
 
 
 @pytest.mark.parametrize("Q,N,D", [(100, 700, 384), (128, 256, 64), (1, 1, 8), (257, 513, 100), (300, 5000, 768)])
-def test_tensorcore_scores_match_bf16_matmul(Q, N, D):
+def test_tensorcore_scores_match_bf16_matmul(Q, N, D, ctas):
     """K1 + K2 (dense debug epilogue): TMA/UMMA descriptors, swizzle, TMEM layout, ragged tiles."""
     import qst_b200
     from qst_b200 import scoring
@@ -71,7 +78,7 @@ def _oracle_topk(q, c, k, score="cos_sim", chunk=50000):
 @pytest.mark.parametrize("Q,N,D,k", [(1000, 10000, 384, 10), (64, 3000, 768, 100), (200, 20000, 96, 100),
                                      (5, 40, 16, 10), (130, 257, 33, 7)])
 @pytest.mark.parametrize("score", ["cos_sim", "dot_score"])
-def test_topk_matches_oracle(Q, N, D, k, score):
+def test_topk_matches_oracle(Q, N, D, k, score, ctas):
     import qst_b200
     g = torch.Generator().manual_seed(14 + Q)
     q = torch.randn(Q, D, generator=g)
@@ -79,6 +86,7 @@ def test_topk_matches_oracle(Q, N, D, k, score):
     want_val, want_idx = _oracle_topk(q, c, k, score)
     index = qst_b200.CorpusIndex(c.to(_dev()), score)
     res = qst_b200.topk(q.to(_dev()), index, k)
+    assert res.plan.ctas == ctas
     if score == "dot_score":
         scale = float(want_val.abs().max())
         torch.testing.assert_close(res.values.cpu() / scale, want_val / scale, rtol=0, atol=2e-6)
