@@ -63,6 +63,7 @@ struct ScoreParams {
   int* unit_cnt;       // [units*UNIT_ROWS]
   uint2* unit_cand;    // [units*UNIT_ROWS*cap]  (key, corpus row)
   float* dense_out;    // dense mode only: [Q, N]
+  int debug;           // QST_SCORE_DEBUG ablation bits (0 in production), see launch_score()
 };
 
 // ------------------------------------------------------------------------------------------
@@ -136,6 +137,77 @@ __device__ __forceinline__ uint32_t warp_select_compact(uint2* __restrict__ buf,
   return T;
 }
 
+// ------------------------------------------------------------------------------------------
+// One 32-row x 32-column block of scores held by a warp (lane = query row, v[j] = column col0+j).
+// Fast path: per-lane max against the row threshold, one ballot, nothing else.
+// Slow path (some lane has a score above its threshold): the lanes with hits park their 32 values
+// in a warp-private shared tile; the warp then serves one hit row at a time -- lane j looks at
+// column j of that row, a ballot ranks the survivors and they are appended to the row's candidate
+// buffer with consecutive (coalesced) stores.  No per-element branches, no dynamic register indexing.
+// ------------------------------------------------------------------------------------------
+constexpr int kStagePitch = 33;  // floats per staged row: conflict-free for both access patterns
+
+template <bool DENSE>
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, const ScoreParams& P, int grow, bool row_ok,
+                                               float& thr, int& cnt, uint2* my_buf, float* stage, int* hist, int lane) {
+  if (P.debug & 2) {  // ablation: TMEM reads only
+    if (v[0] == 0x7fc12345u) P.unit_cnt[0] = 1;
+    return;
+  }
+  if (col0 + 32 > P.N) {  // ragged last tile: columns >= N were zero-filled by TMA
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j >= P.N) v[j] = 0xff800000u;  // -inf
+  }
+  if (DENSE) {
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < P.N) P.dense_out[(size_t)grow * P.N + col0 + j] = __uint_as_float(v[j]);
+    }
+    return;
+  }
+  float mx = __uint_as_float(v[0]);
+#pragma unroll
+  for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+  const bool hit = mx > thr;
+  unsigned hm = __ballot_sync(0xffffffffu, hit);
+  if (hm == 0u) return;
+  if (hit) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
+  }
+  __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
+  while (hm) {
+    const int r = __ffs(hm) - 1;
+    hm &= hm - 1;
+    const float thr_r = __shfl_sync(0xffffffffu, thr, r);
+    const int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
+    uint2* buf_r = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r));
+    const float val = stage[r * kStagePitch + lane];
+    const bool p = val > thr_r;
+    const unsigned pm = __ballot_sync(0xffffffffu, p);
+    if (p) buf_r[cnt_r + __popc(pm & lt)] = make_uint2(float_to_key(val), (uint32_t)(col0 + lane));
+    if (lane == r) cnt += __popc(pm);
+  }
+  __syncwarp();
+  // keep room for the next chunk's worst case (32 appends)
+  unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
+  while (need) {
+    const int r = __ffs(need) - 1;
+    need &= need - 1;
+    const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
+    const int n = __shfl_sync(0xffffffffu, cnt, r);
+    const uint32_t T = warp_select_compact(reinterpret_cast<uint2*>(bp), n, P.kprime, hist, lane);
+    if (lane == r) {
+      cnt = P.kprime;
+      thr = fmaxf(thr, key_to_float(T));
+      atomicMax(&P.thr_hint[grow], T);
+    }
+  }
+}
+
 template <int CTAS, bool DENSE>
 __global__ void __launch_bounds__(kScoreThreads, 1)
 score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
@@ -150,6 +222,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __shared__ __align__(8) uint64_t s_tmem_empty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_hist[4][256];
+  __shared__ float s_stage[4][32 * kStagePitch];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,7 +264,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
       const int q_row = m * C::UNIT_ROWS + (int)rank * BM;
       for (int t = t0; t < t1; ++t) {
-        const int c_row = t * BN + (int)rank * C::B_ROWS;
+        const int c_row = (P.debug & 4) ? 0 : t * BN + (int)rank * C::B_ROWS;
         for (int kb = 0; kb < P.num_kb; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
           const uint32_t full = ptx::smem_u32(&s_full[stage]);
@@ -235,6 +308,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the addr>>4 field
             const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            if ((P.debug & 8) && k != 0) continue;
             if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
             else ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
           }
@@ -255,6 +329,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
     const int row_in_unit = (int)rank * BM + quarter * 32 + lane;
     int* hist = s_hist[quarter];
+    float* stage = s_stage[quarter];
     uint32_t acc = 0, acc_phase = 0;
     for (int u = group; u < P.units; u += n_groups) {
       const int s = u / P.m_tiles, m = u - s * P.m_tiles;
@@ -265,20 +340,40 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       float thr = row_ok ? -INFINITY : INFINITY;
       int cnt = 0;
       uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * C::UNIT_ROWS + row_in_unit) * (size_t)P.cap;
+      uint32_t next_hint = (!DENSE && row_ok) ? __ldcg(&P.thr_hint[grow]) : 0u;
       for (int t = t0; t < t1; ++t) {
-        if (!DENSE && row_ok) {  // pick up thresholds published by other units of this row
-          const uint32_t hk = __ldcg(&P.thr_hint[grow]);
-          if (hk != 0u) thr = fmaxf(thr, key_to_float(hk));
+        if (!DENSE && row_ok) {
+          // thresholds published by other units of this row; the load was issued one tile ago
+          if (next_hint != 0u) thr = fmaxf(thr, key_to_float(next_hint));
+          next_hint = __ldcg(&P.thr_hint[grow]);
         }
         ptx::mbar_wait(ptx::smem_u32(&s_tmem_full[acc]), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+        if (P.debug & 1) {  // ablation: no TMEM reads at all
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
+            else ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
+          }
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+          continue;
+        }
+        // software pipeline over the 8 chunks of 32 columns: the TMEM load of chunk c+1 is in
+        // flight while chunk c is filtered (two register buffers, loop unrolled by 2)
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32(taddr, va);
+        ptx::tmem_ld_wait();
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + chunk * 32, v);
+        for (int chunk = 0; chunk < BN / 32; chunk += 2) {
+          ptx::tmem_ld_32x32(taddr + (chunk + 1) * 32, vb);
+          epilogue_chunk<DENSE>(va, t * BN + chunk * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane);
           ptx::tmem_ld_wait();
-          if (chunk == BN / 32 - 1) {
+          if (chunk + 2 < BN / 32) {
+            ptx::tmem_ld_32x32(taddr + (chunk + 2) * 32, va);
+          } else {
             // every column of this accumulator is now in registers: hand TMEM back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
@@ -287,47 +382,8 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               else ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
             }
           }
-          const int col0 = t * BN + chunk * 32;
-          if (col0 + 32 > P.N) {  // ragged last tile: columns >= N were zero-filled by TMA
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j >= P.N) v[j] = 0xff800000u;  // -inf
-          }
-          if (DENSE) {
-            if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < P.N) P.dense_out[(size_t)grow * P.N + col0 + j] = __uint_as_float(v[j]);
-            }
-          } else {
-            float mx = __uint_as_float(v[0]);
-#pragma unroll
-            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-            if (mx > thr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sc = __uint_as_float(v[j]);
-                if (sc > thr) {
-                  my_buf[cnt] = make_uint2(float_to_key(sc), (uint32_t)(col0 + j));
-                  ++cnt;
-                }
-              }
-            }
-            // keep room for the next chunk's worst case (32 appends)
-            unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
-            while (need) {
-              const int r = __ffs(need) - 1;
-              need &= need - 1;
-              const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
-              const int n = __shfl_sync(0xffffffffu, cnt, r);
-              const uint32_t T = warp_select_compact(reinterpret_cast<uint2*>(bp), n, P.kprime, hist, lane);
-              if (lane == r) {
-                cnt = P.kprime;
-                thr = fmaxf(thr, key_to_float(T));
-                atomicMax(&P.thr_hint[grow], T);
-              }
-            }
-          }
+          epilogue_chunk<DENSE>(vb, t * BN + (chunk + 1) * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane);
+          if (chunk + 2 < BN / 32) ptx::tmem_ld_wait();
         }
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
@@ -409,8 +465,14 @@ static int launch_score_t(const void* q_bf16, const void* c_bf16, const ScorePar
   return QST_OK;
 }
 
-static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P,
+static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P_in,
                         int64_t d_pad, int groups, cudaStream_t st) {
+  // QST_SCORE_DEBUG: performance ablations only (results are wrong when set): 1 = epilogue skips
+  // TMEM reads, 2 = epilogue reads TMEM but does not select, 4 = every tile loads corpus rows 0..255,
+  // 8 = one MMA per k-block instead of four.
+  ScoreParams P = P_in;
+  const char* dbg = getenv("QST_SCORE_DEBUG");
+  P.debug = dbg ? atoi(dbg) : 0;
   if (ctas == 2) {
     return dense ? launch_score_t<2, true>(q_bf16, c_bf16, P, d_pad, groups, st)
                  : launch_score_t<2, false>(q_bf16, c_bf16, P, d_pad, groups, st);
