@@ -141,12 +141,13 @@ int qst_prep_rows(const void* x, int dtype, int64_t n, int64_t d, int normalize,
  * ------------------------------------------------------------------------------------------ */
 typedef struct qst_topk_plan {
   int64_t Q, N, D, D_pad;
-  int32_t k, kprime, cap;        /* cap = per-row candidate capacity of one work unit */
+  int32_t k, kprime;             /* kprime = candidates rescored exactly per query */
+  int32_t kunit, cap;            /* entries one work unit keeps per row; its buffer capacity */
   int32_t m_tiles, n_tiles, stripes, tiles_per_stripe, units;
   int32_t grid, score;           /* grid = CTA groups launched (x ctas CTAs each) */
   int32_t ctas, rows_per_unit;   /* CTAs per tile (2 = cta_group::2 pairs), query rows per work unit */
   size_t ws_bytes;
-  size_t off_thr, off_cnt, off_cand; /* layout inside the workspace */
+  size_t off_thr, off_cnt, off_uthr, off_cand; /* layout inside the workspace */
 } qst_topk_plan;
 
 /* Fills `plan` for (Q queries, N corpus rows, D dims, top k).  kprime <= 0 picks the default

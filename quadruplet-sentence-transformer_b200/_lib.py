@@ -36,12 +36,12 @@ class QuadParams(C.Structure):
 
 class TopkPlan(C.Structure):
     _fields_ = [("Q", C.c_int64), ("N", C.c_int64), ("D", C.c_int64), ("D_pad", C.c_int64),
-                ("k", C.c_int32), ("kprime", C.c_int32), ("cap", C.c_int32),
+                ("k", C.c_int32), ("kprime", C.c_int32), ("kunit", C.c_int32), ("cap", C.c_int32),
                 ("m_tiles", C.c_int32), ("n_tiles", C.c_int32), ("stripes", C.c_int32),
                 ("tiles_per_stripe", C.c_int32), ("units", C.c_int32),
                 ("grid", C.c_int32), ("score", C.c_int32),
                 ("ctas", C.c_int32), ("rows_per_unit", C.c_int32),
-                ("ws_bytes", C.c_size_t), ("off_thr", C.c_size_t), ("off_cnt", C.c_size_t),
+                ("ws_bytes", C.c_size_t), ("off_thr", C.c_size_t), ("off_cnt", C.c_size_t), ("off_uthr", C.c_size_t),
                 ("off_cand", C.c_size_t)]
 
 

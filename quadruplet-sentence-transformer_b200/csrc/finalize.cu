@@ -132,6 +132,7 @@ struct FinParams {
   int sm_cap;  // smem candidate capacity (entries)
   const uint32_t* thr_hint;
   const int* unit_cnt;
+  const uint32_t* unit_thr;
   const uint2* unit_cand;
   const float *q_f32, *q_inv, *q_err, *c_f32, *c_inv, *c_stats;
   int64_t idx_offset;
@@ -171,11 +172,13 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
 
   // 1. gather the candidates of every stripe; compact to the best k' whenever smem fills up
   bool reduced = false;
-  uint32_t T = 0;
+  uint32_t T = 0;      // k'-th largest key among the gathered candidates (once anything is dropped here)
+  uint32_t Tstar = 0;  // largest final unit threshold: upper bound of everything K2 discarded
   int fill = 0;
   for (int s = 0; s < P.stripes; ++s) {
     const size_t urow = (size_t)(s * P.m_tiles + m) * P.rows_per_unit + r;
     const int cnt = P.unit_cnt[urow];
+    Tstar = max(Tstar, P.unit_thr[urow]);
     if (fill + cnt > P.sm_cap) {
       T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
       fill = P.kprime;
@@ -194,22 +197,11 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
     T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
     fill = P.kprime;
     reduced = true;
-  } else if (fill == P.kprime && !reduced) {
-    // nothing dropped here, but the epilogue may have dropped scores below the row threshold:
-    // the k'-th key is then the smallest one present
-    uint32_t mn = 0xffffffffu;
-    for (int i = tid; i < fill; i += kFinThreads) mn = min(mn, keys[i]);
-    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    __shared__ uint32_t s_mn[kFinWarps];
-    if (lane == 0) s_mn[warp] = mn;
-    __syncthreads();
-    mn = s_mn[0];
-    for (int w = 1; w < kFinWarps; ++w) mn = min(mn, s_mn[w]);
-    T = mn;
-    reduced = true;
   }
   const int ncand = fill;  // <= kprime
-  const float t_bf = reduced ? key_to_float(T) : -INFINITY;
+  // every document that is NOT rescored below has a bf16 score <= t_bf
+  const uint32_t Tmax = reduced ? max(T, Tstar) : Tstar;
+  const float t_bf = key_to_float(Tmax);
 
   // 2. exact fp32 rescoring: one warp per candidate, 128-bit loads of the corpus row
   float* exact = reinterpret_cast<float*>(keys);  // keys are no longer needed after selection
@@ -237,7 +229,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   }
   if (P.out_margin && tid == 0) {
     float margin = INFINITY;
-    if (reduced && ncand >= kk) {
+    if (ncand >= kk && t_bf > -INFINITY) {
       // rigorous bound on |bf16 tensor-core score - exact score| for this query against any row:
       //   |dq.c| + |q.dc| + |dq.dc| <= eq*cn + qn*ec + eq*ec      (Cauchy-Schwarz)
       //   + fp32 accumulation inside the tensor core: <= D * 2^-23 * qn * cn
@@ -444,6 +436,7 @@ extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspac
   P.sm_cap = sm_cap;
   P.thr_hint = reinterpret_cast<const uint32_t*>(ws + plan->off_thr);
   P.unit_cnt = reinterpret_cast<const int*>(ws + plan->off_cnt);
+  P.unit_thr = reinterpret_cast<const uint32_t*>(ws + plan->off_uthr);
   P.unit_cand = reinterpret_cast<const uint2*>(ws + plan->off_cand);
   P.q_f32 = q_f32; P.q_inv = q_inv; P.q_err = q_err; P.c_f32 = c_f32; P.c_inv = c_inv; P.c_stats = c_stats;
   P.idx_offset = idx_offset; P.out_val = out_val; P.out_idx = out_idx; P.out_margin = out_margin;

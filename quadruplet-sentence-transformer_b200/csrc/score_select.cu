@@ -58,9 +58,10 @@ struct Cfg {
 struct ScoreParams {
   int Q, N, num_kb;
   int m_tiles, n_tiles, stripes, tiles_per_stripe, units;
-  int kprime, cap;
+  int kunit, cap;      // entries a unit keeps per row after a compaction; buffer capacity
   uint32_t* thr_hint;  // [m_tiles*UNIT_ROWS] ordered keys, 0 = no threshold yet
   int* unit_cnt;       // [units*UNIT_ROWS]
+  uint32_t* unit_thr;  // [units*UNIT_ROWS] final threshold key of the unit row (upper bound of its discards)
   uint2* unit_cand;    // [units*UNIT_ROWS*cap]  (key, corpus row)
   float* dense_out;    // dense mode only: [Q, N]
   int debug;           // QST_SCORE_DEBUG ablation bits (0 in production), see launch_score()
@@ -199,9 +200,9 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
     need &= need - 1;
     const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
     const int n = __shfl_sync(0xffffffffu, cnt, r);
-    const uint32_t T = warp_select_compact(reinterpret_cast<uint2*>(bp), n, P.kprime, hist, lane);
+    const uint32_t T = warp_select_compact(reinterpret_cast<uint2*>(bp), n, P.kunit, hist, lane);
     if (lane == r) {
-      cnt = P.kprime;
+      cnt = P.kunit;
       thr = fmaxf(thr, key_to_float(T));
       atomicMax(&P.thr_hint[grow], T);
     }
@@ -388,7 +389,10 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (!DENSE) P.unit_cnt[(size_t)u * C::UNIT_ROWS + row_in_unit] = cnt;
+      if (!DENSE) {
+        P.unit_cnt[(size_t)u * C::UNIT_ROWS + row_in_unit] = cnt;
+        P.unit_thr[(size_t)u * C::UNIT_ROWS + row_in_unit] = row_ok ? float_to_key(thr) : 0u;
+      }
     }
   }
 
@@ -519,7 +523,7 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   QST_CHECK_ARG(kprime >= k && kprime <= 2048, "plan_make: kprime %d out of range [k, 2048]", kprime);
   memset(plan, 0, sizeof(*plan));
   plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim(D);
-  plan->k = k; plan->kprime = kprime; plan->cap = 2 * kprime;
+  plan->k = k; plan->kprime = kprime;
   plan->score = score;
   plan->ctas = default_ctas();
   plan->rows_per_unit = BM * plan->ctas;
@@ -544,11 +548,24 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   plan->tiles_per_stripe = (int)ceil_div(plan->n_tiles, best_s);
   plan->stripes = (int)ceil_div(plan->n_tiles, plan->tiles_per_stripe);
   plan->units = plan->m_tiles * plan->stripes;
+  // Entries a unit keeps per row.  The certificate only needs every unit's final threshold to stay
+  // below the k'-th best score overall, so with S stripes a unit needs ~k'/S entries plus slack
+  // for uneven placement; QST_KUNIT overrides (kunit = kprime is the most conservative setting).
+  {
+    int ku = (int)round_up(2 * (int)ceil_div(kprime, plan->stripes) + 16, 32);
+    if (ku < 32) ku = 32;
+    if (ku > kprime) ku = kprime;
+    const char* e = getenv("QST_KUNIT");
+    if (e && atoi(e) >= 32) { ku = (int)round_up(atoi(e), 32); if (ku > kprime) ku = kprime; }
+    plan->kunit = ku;
+    plan->cap = 2 * ku > ku + 96 ? 2 * ku : ku + 96;
+  }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
   size_t off = 0;
   const size_t ur = (size_t)plan->rows_per_unit;
   plan->off_thr = off;  off += round_up((size_t)plan->m_tiles * ur * sizeof(uint32_t), 256);
   plan->off_cnt = off;  off += round_up((size_t)plan->units * ur * sizeof(int), 256);
+  plan->off_uthr = off; off += round_up((size_t)plan->units * ur * sizeof(uint32_t), 256);
   plan->off_cand = off; off += (size_t)plan->units * ur * (size_t)plan->cap * sizeof(uint2);
   plan->ws_bytes = off;
   return QST_OK;
@@ -565,9 +582,10 @@ extern "C" int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, c
   P.Q = (int)plan->Q; P.N = (int)plan->N; P.num_kb = (int)(plan->D_pad / BK);
   P.m_tiles = plan->m_tiles; P.n_tiles = plan->n_tiles; P.stripes = plan->stripes;
   P.tiles_per_stripe = plan->tiles_per_stripe; P.units = plan->units;
-  P.kprime = plan->kprime; P.cap = plan->cap;
+  P.kunit = plan->kunit; P.cap = plan->cap;
   P.thr_hint = reinterpret_cast<uint32_t*>(ws + plan->off_thr);
   P.unit_cnt = reinterpret_cast<int*>(ws + plan->off_cnt);
+  P.unit_thr = reinterpret_cast<uint32_t*>(ws + plan->off_uthr);
   P.unit_cand = reinterpret_cast<uint2*>(ws + plan->off_cand);
   QST_CHECK_ARG(plan->ctas == 1 || plan->ctas == 2, "score_select: plan->ctas must be 1 or 2");
   QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * plan->rows_per_unit * sizeof(uint32_t), st));
