@@ -168,9 +168,14 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
     }
     return;
   }
-  float mx = __uint_as_float(v[0]);
+  // row maximum as a shallow tree (3-input max): the epilogue runs one warp per scheduler, so the
+  // dependency depth of this reduction is paid in full
+  float m8[8];
 #pragma unroll
-  for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+  for (int g = 0; g < 8; ++g)
+    m8[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
+                  fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+  const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
   const bool hit = mx > thr;
   unsigned hm = __ballot_sync(0xffffffffu, hit);
   if (hm == 0u) return;

@@ -31,10 +31,14 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
 def all_gather_topk(vals: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """[Q, k] per rank -> [G, Q, k] on every rank (rank-major).  Works on any backend."""
     world = dist.get_world_size(group)
-    gv = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
-    gi = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(gv, vals.contiguous(), group=group)
-    dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
+    vals, idx = vals.contiguous(), idx.contiguous()
+    # flat [G*Q, k] outputs (concatenation along dim 0) are accepted by both nccl and gloo
+    gv = torch.empty((world * vals.shape[0],) + tuple(vals.shape[1:]), dtype=vals.dtype, device=vals.device)
+    gi = torch.empty((world * idx.shape[0],) + tuple(idx.shape[1:]), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(gv, vals, group=group)
+    dist.all_gather_into_tensor(gi, idx, group=group)
+    gv = gv.view((world,) + tuple(vals.shape))
+    gi = gi.view((world,) + tuple(idx.shape))
     return gv, gi
 
 

