@@ -139,6 +139,88 @@ __device__ __forceinline__ uint32_t warp_select_compact(uint2* __restrict__ buf,
 }
 
 // ------------------------------------------------------------------------------------------
+// Register-resident compaction for buffers of at most 256 entries (8 per lane): ONE round trip to
+// the buffer, a 256-bin histogram over the observed key range, keep every entry in or above the
+// bin in which the running count (from the top) reaches k.  Keeps >= k entries (k plus whatever
+// shares the boundary bin), drops only entries strictly below the returned threshold T.  Returns
+// false (buffer untouched) when the histogram cannot separate the keys enough to free space, in
+// which case the caller falls back to the exact radix select.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallCap = 256;
+
+__device__ __forceinline__ bool warp_compact_small(uint2* __restrict__ buf, int n, int k, int max_keep, int* hist,
+                                                   int lane, uint32_t& T_out, int& n_out) {
+  uint2 e[kSmallCap / 32];
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int i = 0; i < kSmallCap / 32; ++i) {
+    const int j = lane + 32 * i;
+    e[i] = make_uint2(0u, 0u);
+    if (j < n) {
+      e[i] = buf[j];
+      lo = min(lo, e[i].x);
+      hi = max(hi, e[i].x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  const uint64_t span = (uint64_t)(hi - lo) + 1ull;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+  __syncwarp();
+  int bin[kSmallCap / 32];
+#pragma unroll
+  for (int i = 0; i < kSmallCap / 32; ++i) {
+    bin[i] = (int)(((uint64_t)(e[i].x - lo) << 8) / span);   // monotone in the key, 0..255
+    if (lane + 32 * i < n) atomicAdd(&hist[bin[i]], 1);
+  }
+  __syncwarp();
+  int c[8], ls = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; ls += c[i]; }
+  int incl = ls;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  const int above = incl - ls;
+  const bool mine = (above < k) && (k <= above + ls);
+  const unsigned who = __ballot_sync(0xffffffffu, mine);
+  const int src = 31 - __clz(who);
+  int bstar = 0, kept = 0;
+  if (lane == src) {
+    int run = above;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      if (run < k && k <= run + c[i]) { bstar = lane * 8 + i; kept = run + c[i]; }
+      run += c[i];
+    }
+  }
+  bstar = __shfl_sync(0xffffffffu, bstar, src);
+  kept = __shfl_sync(0xffffffffu, kept, src);
+  __syncwarp();
+  if (kept > max_keep) return false;
+  // smallest key that maps to bin bstar: everything dropped is strictly below it
+  T_out = lo + (uint32_t)((((uint64_t)bstar * span) + 255ull) >> 8);
+  const unsigned lt = (1u << lane) - 1u;
+  int w = 0;
+#pragma unroll
+  for (int i = 0; i < kSmallCap / 32; ++i) {
+    const bool keep = (lane + 32 * i < n) && (bin[i] >= bstar);
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[w + __popc(km & lt)] = e[i];
+    w += __popc(km);
+  }
+  __syncwarp();
+  n_out = w;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // One 32-row x 32-column block of scores held by a warp (lane = query row, v[j] = column col0+j).
 // Fast path: per-lane max against the row threshold, one ballot, nothing else.
 // Slow path (some lane has a score above its threshold): the lanes with hits park their 32 values
@@ -203,11 +285,18 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   while (need) {
     const int r = __ffs(need) - 1;
     need &= need - 1;
-    const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
+    uint2* bp = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r));
     const int n = __shfl_sync(0xffffffffu, cnt, r);
-    const uint32_t T = warp_select_compact(reinterpret_cast<uint2*>(bp), n, P.kunit, hist, lane);
+    uint32_t T = 0u;
+    int n_new = P.kunit;
+    // fast: one-pass histogram compaction in registers (must leave room for >= 64 more appends);
+    // exact 4-pass radix select otherwise (large buffers, or keys the histogram cannot separate)
+    if (!(P.cap <= kSmallCap && warp_compact_small(bp, n, P.kunit, P.cap - 96, hist, lane, T, n_new))) {
+      T = warp_select_compact(bp, n, P.kunit, hist, lane);
+      n_new = P.kunit;
+    }
     if (lane == r) {
-      cnt = P.kunit;
+      cnt = n_new;
       thr = fmaxf(thr, key_to_float(T));
       atomicMax(&P.thr_hint[grow], T);
     }
@@ -563,7 +652,10 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
     const char* e = getenv("QST_KUNIT");
     if (e && atoi(e) >= 32) { ku = (int)round_up(atoi(e), 32); if (ku > kprime) ku = kprime; }
     plan->kunit = ku;
+    // slack between compactions: at least 96 entries, and the whole 256-entry register-resident
+    // compaction window when the unit keeps few entries
     plan->cap = 2 * ku > ku + 96 ? 2 * ku : ku + 96;
+    if (ku <= 128 && plan->cap < 256) plan->cap = 256;
   }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
   size_t off = 0;
