@@ -220,6 +220,31 @@ __device__ __forceinline__ bool warp_compact_small(uint2* __restrict__ buf, int 
   return true;
 }
 
+// Compacts the candidate buffers of the rows in `need` (one bit per lane) down to ~kunit entries
+// and publishes each row's new threshold to the hint array.
+__device__ __forceinline__ void compact_rows(unsigned need, int max_keep, const ScoreParams& P, int grow, float& thr,
+                                             int& cnt, uint2* my_buf, int* hist, int lane) {
+  while (need) {
+    const int r = __ffs(need) - 1;
+    need &= need - 1;
+    uint2* bp = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r));
+    const int n = __shfl_sync(0xffffffffu, cnt, r);
+    uint32_t T = 0u;
+    int n_new = P.kunit;
+    // fast: one-pass histogram compaction in registers; exact 4-pass radix select otherwise
+    // (large buffers, or keys the histogram cannot separate)
+    if (!(P.cap <= kSmallCap && warp_compact_small(bp, n, P.kunit, max_keep, hist, lane, T, n_new))) {
+      T = warp_select_compact(bp, n, P.kunit, hist, lane);
+      n_new = P.kunit;
+    }
+    if (lane == r) {
+      cnt = n_new;
+      thr = fmaxf(thr, key_to_float(T));
+      atomicMax(&P.thr_hint[grow], T);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // One 32-row x 32-column block of scores held by a warp (lane = query row, v[j] = column col0+j).
 // Fast path: per-lane max against the row threshold, one ballot, nothing else.
@@ -267,40 +292,38 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   }
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
+  // four hit rows per trip: the four shuffle/load/ballot chains are independent, which hides their
+  // latency (the epilogue has a single warp per scheduler)
   while (hm) {
-    const int r = __ffs(hm) - 1;
-    hm &= hm - 1;
-    const float thr_r = __shfl_sync(0xffffffffu, thr, r);
-    const int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
-    uint2* buf_r = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r));
-    const float val = stage[r * kStagePitch + lane];
-    const bool p = val > thr_r;
-    const unsigned pm = __ballot_sync(0xffffffffu, p);
-    if (p) buf_r[cnt_r + __popc(pm & lt)] = make_uint2(float_to_key(val), (uint32_t)(col0 + lane));
-    if (lane == r) cnt += __popc(pm);
+    int r[4];
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ok[i] = hm != 0u;
+      r[i] = ok[i] ? __ffs(hm) - 1 : 0;
+      hm &= hm - 1;          // 0 stays 0
+    }
+    float thr_r[4], val[4];
+    int cnt_r[4];
+    uint2* buf_r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      thr_r[i] = __shfl_sync(0xffffffffu, thr, r[i]);
+      cnt_r[i] = __shfl_sync(0xffffffffu, cnt, r[i]);
+      buf_r[i] = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r[i]));
+      val[i] = stage[r[i] * kStagePitch + lane];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool p = ok[i] && (val[i] > thr_r[i]);
+      const unsigned pm = __ballot_sync(0xffffffffu, p);
+      if (p) buf_r[i][cnt_r[i] + __popc(pm & lt)] = make_uint2(float_to_key(val[i]), (uint32_t)(col0 + lane));
+      if (ok[i] && lane == r[i]) cnt += __popc(pm);
+    }
   }
   __syncwarp();
   // keep room for the next chunk's worst case (32 appends)
-  unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
-  while (need) {
-    const int r = __ffs(need) - 1;
-    need &= need - 1;
-    uint2* bp = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r));
-    const int n = __shfl_sync(0xffffffffu, cnt, r);
-    uint32_t T = 0u;
-    int n_new = P.kunit;
-    // fast: one-pass histogram compaction in registers (must leave room for >= 64 more appends);
-    // exact 4-pass radix select otherwise (large buffers, or keys the histogram cannot separate)
-    if (!(P.cap <= kSmallCap && warp_compact_small(bp, n, P.kunit, P.cap - 96, hist, lane, T, n_new))) {
-      T = warp_select_compact(bp, n, P.kunit, hist, lane);
-      n_new = P.kunit;
-    }
-    if (lane == r) {
-      cnt = n_new;
-      thr = fmaxf(thr, key_to_float(T));
-      atomicMax(&P.thr_hint[grow], T);
-    }
-  }
+  compact_rows(__ballot_sync(0xffffffffu, cnt > P.cap - 32), P.cap - 96, P, grow, thr, cnt, my_buf, hist, lane);
 }
 
 template <int CTAS, bool DENSE>
@@ -484,6 +507,9 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (acc == 0) acc_phase ^= 1u;
       }
       if (!DENSE) {
+        // leave ~kunit entries per row and publish the unit's final threshold: later units of the
+        // same rows start from it, and K3 has less to gather
+        compact_rows(__ballot_sync(0xffffffffu, cnt > P.kunit), P.cap, P, grow, thr, cnt, my_buf, hist, lane);
         P.unit_cnt[(size_t)u * C::UNIT_ROWS + row_in_unit] = cnt;
         P.unit_thr[(size_t)u * C::UNIT_ROWS + row_in_unit] = row_ok ? float_to_key(thr) : 0u;
       }
@@ -652,10 +678,8 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
     const char* e = getenv("QST_KUNIT");
     if (e && atoi(e) >= 32) { ku = (int)round_up(atoi(e), 32); if (ku > kprime) ku = kprime; }
     plan->kunit = ku;
-    // slack between compactions: at least 96 entries, and the whole 256-entry register-resident
-    // compaction window when the unit keeps few entries
+    // slack between compactions: at least 96 entries
     plan->cap = 2 * ku > ku + 96 ? 2 * ku : ku + 96;
-    if (ku <= 128 && plan->cap < 256) plan->cap = 256;
   }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
   size_t off = 0;
