@@ -323,7 +323,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   }
   __syncwarp();
   // keep room for the next chunk's worst case (32 appends)
-  compact_rows(__ballot_sync(0xffffffffu, cnt > P.cap - 32), P.cap - 96, P, grow, thr, cnt, my_buf, hist, lane);
+  compact_rows(__ballot_sync(0xffffffffu, cnt > P.cap - 32), P.cap - 64, P, grow, thr, cnt, my_buf, hist, lane);
 }
 
 template <int CTAS, bool DENSE>
@@ -454,7 +454,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int t0 = s * P.tiles_per_stripe;
       const int t1 = min(t0 + P.tiles_per_stripe, P.n_tiles);
       const int grow = m * C::UNIT_ROWS + row_in_unit;
-      const bool row_ok = grow < P.Q;
+      const bool row_ok = grow < P.Q && !(P.debug & 16);   // ablation 16: no row ever has a hit
       float thr = row_ok ? -INFINITY : INFINITY;
       int cnt = 0;
       uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * C::UNIT_ROWS + row_in_unit) * (size_t)P.cap;
@@ -593,7 +593,7 @@ static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_
                         int64_t d_pad, int groups, cudaStream_t st) {
   // QST_SCORE_DEBUG: performance ablations only (results are wrong when set): 1 = epilogue skips
   // TMEM reads, 2 = epilogue reads TMEM but does not select, 4 = every tile loads corpus rows 0..255,
-  // 8 = one MMA per k-block instead of four.
+  // 8 = one MMA per k-block instead of four, 16 = thresholds at +inf (fast path only).
   ScoreParams P = P_in;
   const char* dbg = getenv("QST_SCORE_DEBUG");
   P.debug = dbg ? atoi(dbg) : 0;
@@ -650,20 +650,31 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   plan->m_tiles = (int)ceil_div(Q, plan->rows_per_unit);
   plan->n_tiles = (int)ceil_div(N, BN);
   const int groups_max = sm_count / plan->ctas > 0 ? sm_count / plan->ctas : 1;
-  // stripes: minimise  waves * (tiles_per_stripe + cold-start cost)  over S
+  // stripes: minimise  waves * (tiles_per_stripe + per-unit cost)  over S, subject to a stripe
+  // being small enough (<= 32 MB of bf16 rows) that the few stripes being walked at any time stay
+  // resident in the 126 MB L2 even when their walkers drift apart
   const int r_min = 4;
   int s_max = plan->n_tiles / r_min;
   if (s_max < 1) s_max = 1;
-  if (s_max > 64) s_max = 64;
+  if (s_max > 128) s_max = 128;
+  const int64_t tile_bytes = (int64_t)BN * plan->D_pad * 2;
+  int64_t r_l2 = (32ll << 20) / tile_bytes;
+  if (r_l2 < r_min) r_l2 = r_min;
+  int s_min = (int)ceil_div(plan->n_tiles, r_l2);
+  if (s_min > s_max) s_min = s_max;
   double best = 1e300;
   int best_s = 1;
-  for (int S = 1; S <= s_max; ++S) {
+  for (int S = s_min; S <= s_max; ++S) {
     const int R = (int)ceil_div(plan->n_tiles, S);
     const int S_eff = (int)ceil_div(plan->n_tiles, R);  // stripes actually non-empty
     const int64_t units = (int64_t)plan->m_tiles * S_eff;
     const int64_t waves = ceil_div(units, groups_max);
     const double cost = (double)waves * ((double)R + 2.0);
     if (cost < best - 1e-9) { best = cost; best_s = S_eff; }
+  }
+  {
+    const char* e = getenv("QST_STRIPES");   // tuning override
+    if (e && atoi(e) >= 1) best_s = atoi(e) < plan->n_tiles ? atoi(e) : plan->n_tiles;
   }
   plan->tiles_per_stripe = (int)ceil_div(plan->n_tiles, best_s);
   plan->stripes = (int)ceil_div(plan->n_tiles, plan->tiles_per_stripe);
@@ -672,14 +683,14 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   // below the k'-th best score overall, so with S stripes a unit needs ~k'/S entries plus slack
   // for uneven placement; QST_KUNIT overrides (kunit = kprime is the most conservative setting).
   {
-    int ku = (int)round_up(2 * (int)ceil_div(kprime, plan->stripes) + 16, 32);
-    if (ku < 32) ku = 32;
+    int ku = (int)round_up(2 * (int)ceil_div(kprime, plan->stripes) + 8, 16);
+    if (ku < 16) ku = 16;
     if (ku > kprime) ku = kprime;
     const char* e = getenv("QST_KUNIT");
-    if (e && atoi(e) >= 32) { ku = (int)round_up(atoi(e), 32); if (ku > kprime) ku = kprime; }
+    if (e && atoi(e) >= 16) { ku = (int)round_up(atoi(e), 16); if (ku > kprime) ku = kprime; }
     plan->kunit = ku;
-    // slack between compactions: at least 96 entries
-    plan->cap = 2 * ku > ku + 96 ? 2 * ku : ku + 96;
+    // slack between compactions: at least 128 entries
+    plan->cap = 2 * ku > ku + 128 ? 2 * ku : ku + 128;
   }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
   size_t off = 0;
