@@ -12,6 +12,7 @@ namespace qst {
 
 constexpr int kFinThreads = 256;
 constexpr int kFinWarps = kFinThreads / 32;
+constexpr int kMaxStripes = 128;  // must cover qst_topk_plan_make's s_max
 
 // ------------------------------------------------------------------------------------------
 // CTA-wide: keep the k largest keys of (keys, idx)[0..n) -> compacted to the front (order
@@ -122,6 +123,34 @@ __device__ __forceinline__ float warp_dot_f32(const float* __restrict__ qrow, co
   return warp_sum(acc);
 }
 
+// Two rows at once: same per-row operation order as warp_dot_f32 (bit-identical results), twice the
+// loads in flight.
+__device__ __forceinline__ void warp_dot_f32_x2(const float* __restrict__ qrow, const float* __restrict__ c0,
+                                                const float* __restrict__ c1, int D, bool vec4, int lane, float& o0,
+                                                float& o1) {
+  float a0 = 0.f, a1 = 0.f;
+  if (vec4) {
+    const float4* p0 = reinterpret_cast<const float4*>(c0);
+    const float4* p1 = reinterpret_cast<const float4*>(c1);
+    const float4* q4 = reinterpret_cast<const float4*>(qrow);
+    for (int i = lane; i < D / 4; i += 32) {
+      const float4 x = __ldg(p0 + i);
+      const float4 y = __ldg(p1 + i);
+      const float4 a = q4[i];
+      a0 = fmaf(a.x, x.x, a0); a0 = fmaf(a.y, x.y, a0); a0 = fmaf(a.z, x.z, a0); a0 = fmaf(a.w, x.w, a0);
+      a1 = fmaf(a.x, y.x, a1); a1 = fmaf(a.y, y.y, a1); a1 = fmaf(a.z, y.z, a1); a1 = fmaf(a.w, y.w, a1);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) {
+      const float a = qrow[i];
+      a0 = fmaf(a, __ldg(c0 + i), a0);
+      a1 = fmaf(a, __ldg(c1 + i), a1);
+    }
+  }
+  o0 = warp_sum(a0);
+  o1 = warp_sum(a1);
+}
+
 __device__ __forceinline__ float apply_score(float dot, int score, float q_inv, const float* c_inv, int row) {
   return score == QST_SCORE_COS ? (dot * q_inv) * (c_inv ? c_inv[row] : 1.0f) : dot;
 }
@@ -175,23 +204,58 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   uint32_t T = 0;      // k'-th largest key among the gathered candidates (once anything is dropped here)
   uint32_t Tstar = 0;  // largest final unit threshold: upper bound of everything K2 discarded
   int fill = 0;
-  for (int s = 0; s < P.stripes; ++s) {
-    const size_t urow = (size_t)(s * P.m_tiles + m) * P.rows_per_unit + r;
-    const int cnt = P.unit_cnt[urow];
-    Tstar = max(Tstar, P.unit_thr[urow]);
-    if (fill + cnt > P.sm_cap) {
-      T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
-      fill = P.kprime;
-      reduced = true;
+  __shared__ int s_cnt[kMaxStripes + 1];
+  __shared__ uint32_t s_tstar;
+  // all stripe counts at once, then every warp copies whole unit buffers in parallel
+  if (tid == 0) s_tstar = 0u;
+  __syncthreads();
+  for (int st = tid; st < P.stripes; st += kFinThreads) {
+    const size_t urow = (size_t)(st * P.m_tiles + m) * P.rows_per_unit + r;
+    s_cnt[st] = P.unit_cnt[urow];
+    atomicMax(&s_tstar, P.unit_thr[urow]);
+  }
+  __syncthreads();
+  if (tid == 0) {  // exclusive prefix (at most kMaxStripes terms)
+    int run = 0;
+    for (int st = 0; st < P.stripes; ++st) { const int c = s_cnt[st]; s_cnt[st] = run; run += c; }
+    s_cnt[P.stripes] = run;
+  }
+  __syncthreads();
+  Tstar = s_tstar;
+  const int total = s_cnt[P.stripes];
+  if (total <= P.sm_cap) {
+    for (int st = warp; st < P.stripes; st += kFinWarps) {
+      const size_t urow = (size_t)(st * P.m_tiles + m) * P.rows_per_unit + r;
+      const int off = s_cnt[st], cnt = s_cnt[st + 1] - off;
+      const uint2* src = P.unit_cand + urow * (size_t)P.cap;
+      for (int i = lane; i < cnt; i += 32) {
+        const uint2 e = src[i];
+        keys[off + i] = e.x;
+        idx[off + i] = (int32_t)e.y;
+      }
     }
-    const uint2* src = P.unit_cand + urow * (size_t)P.cap;
-    for (int i = tid; i < cnt; i += kFinThreads) {
-      const uint2 e = src[i];
-      keys[fill + i] = e.x;
-      idx[fill + i] = (int32_t)e.y;
-    }
-    fill += cnt;
+    fill = total;
     __syncthreads();
+  } else {
+    // rare (very large k'): stream the unit buffers through shared memory, compacting to the best
+    // k' whenever it fills up
+    for (int st = 0; st < P.stripes; ++st) {
+      const size_t urow = (size_t)(st * P.m_tiles + m) * P.rows_per_unit + r;
+      const int cnt = s_cnt[st + 1] - s_cnt[st];
+      if (fill + cnt > P.sm_cap) {
+        T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
+        fill = P.kprime;
+        reduced = true;
+      }
+      const uint2* src = P.unit_cand + urow * (size_t)P.cap;
+      for (int i = tid; i < cnt; i += kFinThreads) {
+        const uint2 e = src[i];
+        keys[fill + i] = e.x;
+        idx[fill + i] = (int32_t)e.y;
+      }
+      fill += cnt;
+      __syncthreads();
+    }
   }
   if (fill > P.kprime) {
     T = block_select_topk(keys, idx, fill, P.kprime, tmp_keys, tmp_idx, hist, s_misc);
@@ -208,10 +272,21 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   __syncthreads();
   const float qi = (P.score == QST_SCORE_COS && P.q_inv) ? P.q_inv[q] : 1.0f;
   const bool vec4 = (P.D % 4) == 0 && ((reinterpret_cast<uintptr_t>(P.c_f32) & 15u) == 0);
-  for (int j = warp; j < ncand; j += kFinWarps) {
-    const int ci = idx[j];
-    const float acc = warp_dot_f32(qrow, P.c_f32 + (size_t)ci * P.D, P.D, vec4, lane);
-    if (lane == 0) exact[j] = apply_score(acc, P.score, qi, P.c_inv, ci);
+  for (int j = warp; j < ncand; j += 2 * kFinWarps) {
+    const int j1 = j + kFinWarps;
+    const int c0 = idx[j];
+    if (j1 < ncand) {
+      const int c1 = idx[j1];
+      float d0, d1;
+      warp_dot_f32_x2(qrow, P.c_f32 + (size_t)c0 * P.D, P.c_f32 + (size_t)c1 * P.D, P.D, vec4, lane, d0, d1);
+      if (lane == 0) {
+        exact[j] = apply_score(d0, P.score, qi, P.c_inv, c0);
+        exact[j1] = apply_score(d1, P.score, qi, P.c_inv, c1);
+      }
+    } else {
+      const float d0 = warp_dot_f32(qrow, P.c_f32 + (size_t)c0 * P.D, P.D, vec4, lane);
+      if (lane == 0) exact[j] = apply_score(d0, P.score, qi, P.c_inv, c0);
+    }
   }
   // pad to a power of two for the sort
   int n2 = 1;
@@ -425,6 +500,7 @@ extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspac
                                  float* out_margin, qst_stream_t stream) {
   QST_CHECK_ARG(plan && workspace && q_f32 && c_f32 && out_val && out_idx, "finalize_topk: null argument");
   QST_CHECK_ARG(plan->score != QST_SCORE_COS || (q_inv && c_inv), "finalize_topk: cos score needs inverse norms");
+  QST_CHECK_ARG(plan->stripes <= kMaxStripes, "finalize_topk: too many stripes (%d)", plan->stripes);
   const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
   FinParams P{};
   P.Q = (int)plan->Q; P.N = (int)plan->N; P.D = (int)plan->D;

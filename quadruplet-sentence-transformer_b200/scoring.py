@@ -220,6 +220,19 @@ def _dense_scores(a, b, score: str) -> torch.Tensor:
     return out
 
 
+_pinned_cache = {}
+
+
+def _pinned_outputs(shape):
+    """Reusable pinned host buffers for the ranking (allocating pinned memory costs milliseconds)."""
+    buf = _pinned_cache.get(shape)
+    if buf is None:
+        buf = (torch.empty(shape, dtype=torch.float32, pin_memory=True),
+               torch.empty(shape, dtype=torch.int64, pin_memory=True))
+        _pinned_cache[shape] = buf
+    return buf
+
+
 def topk_host(queries_host: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0,
               exact: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """End-to-end call with HOST buffers: pinned queries in, pinned (values, indices) out.
@@ -230,8 +243,7 @@ def topk_host(queries_host: torch.Tensor, index: CorpusIndex, k: int, kprime: in
     dev = index.device
     q_dev = queries_host.to(dev, non_blocking=True)
     res = topk(q_dev, index, k, kprime, exact)
-    vals = torch.empty(res.values.shape, dtype=torch.float32, pin_memory=True)
-    idx = torch.empty(res.indices.shape, dtype=torch.int64, pin_memory=True)
+    vals, idx = _pinned_outputs(tuple(res.values.shape))
     vals.copy_(res.values, non_blocking=True)
     idx.copy_(res.indices, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
