@@ -270,3 +270,72 @@ def test_host_buffer_entry_and_dense_callable():
     torch.testing.assert_close(dense.cpu(), ir_oracle.cos_sim(q, c), rtol=0, atol=2e-6)
     with pytest.raises(qst_b200.QstError):
         qst_b200.topk(q, index, 10)            # CPU queries: no fallback
+
+
+def test_full_size_config3_properties():
+    """BASELINE.json config 3 at full size (10k x 1M x 768, k=100) through size-independent
+    properties: (a) a sample of queries against the CPU oracle on the full corpus, (b) planted
+    self-matches come back first with score 1, (c) every list is sorted and duplicate-free,
+    (d) every query ends certified, (e) a 4-way sharded run merges to the same answer."""
+    import qst_b200
+    from qst_b200 import sharded
+    Q, N, D, k = 10_000, 1_000_000, 768, 100
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(14)
+    corpus = torch.cat([torch.randn(125_000, D, generator=g, device=dev) for _ in range(N // 125_000)])
+    queries = torch.randn(Q, D, generator=g, device=dev)
+    planted = torch.arange(0, 64, device=dev) * 15_000 + 7            # 64 queries are corpus rows (scaled)
+    queries[:64] = corpus[planted] * 3.0
+    index = qst_b200.CorpusIndex(corpus, "cos_sim")
+    res = qst_b200.topk(queries, index, k)
+    vals, idx = res.values, res.indices
+    assert bool((res.margin > 0).all())                                                   # (d)
+    assert bool((vals[:, :-1] >= vals[:, 1:]).all())                                      # (c)
+    assert bool((idx.sort(dim=1).values.diff(dim=1) > 0).all()) and bool((idx >= 0).all() and (idx < N).all())
+    assert torch.equal(idx[:64, 0], planted) and bool((vals[:64, 0] - 1).abs().max() < 1e-5)  # (b)
+    sample = torch.cat([torch.arange(0, 8), torch.arange(5000, 5008), torch.arange(Q - 8, Q)])
+    want_val, want_idx = _oracle_topk(queries[sample].cpu(), corpus.cpu(), k)             # (a)
+    assert_same_ranking(idx[sample.to(dev)], vals[sample.to(dev)], want_idx, want_val, "config 3 sample")
+    pv, pi = [], []                                                                       # (e)
+    sub = torch.arange(0, Q, 25, device=dev)
+    for r in range(4):
+        s, e = sharded.shard_bounds(N, 4, r)
+        part = qst_b200.topk(queries[sub], qst_b200.CorpusIndex(corpus[s:e], "cos_sim", idx_offset=s), k)
+        pv.append(part.values)
+        pi.append(part.indices)
+    mv, mi = sharded.merge_topk(torch.stack(pv), torch.stack(pi))
+    assert_same_ranking(mi, mv, idx[sub].cpu(), vals[sub].cpu(), "4 shards vs 1")
+
+
+def test_metrics_at_scale_match_reference_loops():
+    """Config-5 style metric suite (MRR@10, NDCG@10, Recall@{1,10,100}, MAP@100) on 50k queries:
+    K4 + host reductions vs the reference's Python loops fed with the same ranking."""
+    import qst_b200
+    from oracle import ir_oracle
+    rng = np.random.default_rng(5)
+    n_q, n_c, K = 50_000, 200_000, 100
+    ranked = rng.integers(0, n_c, size=(n_q, K), dtype=np.int64)
+    rel_first = rng.integers(0, n_c, size=(n_q, 8), dtype=np.int64)
+    # make ~half of the queries have hits at random ranks
+    rows = rng.choice(n_q, n_q // 2, replace=False)
+    ranked[rows, rng.integers(0, K, size=rows.size)] = rel_first[rows, 0]
+    ranked[rows[: n_q // 4], rng.integers(0, 10, size=n_q // 4)] = rel_first[rows[: n_q // 4], 1]
+    queries = {str(i): str(i) for i in range(n_q)}
+    relevant = {str(i): {str(j) for j in rel_first[i]} for i in range(n_q)}
+    k_lists = dict(mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1, 10], precision_recall_at_k=[1, 10, 100],
+                   map_at_k=[100])
+    ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, {}, relevant, write_csv=False,
+                                                        score_functions={"cos_sim": ir_oracle.cos_sim}, **k_lists)
+    hits = [[{"corpus_id": str(j), "score": float(K - r)} for r, j in enumerate(row)] for row in ranked.tolist()]
+    want = ref.compute_metrics(hits)
+    from qst_b200 import metrics
+    rel_pos = [sorted(int(j) for j in rel_first[i]) for i in range(n_q)]
+    rel_pos = [sorted(set(r)) for r in rel_pos]
+    rowptr, cols = metrics.relevance_csr(rel_pos, _dev())
+    ks = sorted({k for v in k_lists.values() for k in v})
+    per_query = metrics.per_query_metrics(torch.from_numpy(ranked).to(_dev()), rowptr, cols, ks).cpu().numpy()
+    got = metrics.reduce_like_reference(per_query, ks, k_lists["accuracy_at_k"], k_lists["precision_recall_at_k"],
+                                        k_lists["mrr_at_k"], k_lists["ndcg_at_k"], k_lists["map_at_k"])
+    for metric in want:
+        for k, v in want[metric].items():
+            assert float(got[metric][k]) == float(v), (metric, k, got[metric][k], v)
