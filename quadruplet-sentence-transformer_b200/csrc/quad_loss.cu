@@ -312,6 +312,171 @@ __global__ void __launch_bounds__(kQuadThreads) quad_kernel(const QuadArgs g) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident fused forward+backward for rows of at most 32*VEC*kRegChunks elements
+// (1024 fp32 / 2048 half): the four rows are loaded ONCE with every 128-bit load issued up front
+// (kRegChunks*4 independent loads per thread), distances, loss terms and all four gradients are
+// computed from registers.  HBM traffic = the algorithmic 8*B*D*sizeof(T), nothing re-read.
+// ------------------------------------------------------------------------------------------
+constexpr int kRegChunks = 8;
+
+template <typename T, int PM>
+__global__ void __launch_bounds__(kQuadThreads) quad_fused_reg_kernel(const QuadArgs g) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int kWarps = kQuadThreads / 32;
+  const int64_t D = g.D;
+  const float inv_b = g.reduction == QST_RED_MEAN ? 1.0f / (float)g.B : 1.0f;
+  const float eps = g.prm.eps, p = g.prm.p;
+  const bool swap = g.prm.swap != 0;
+  double block_sum = 0.0;
+
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < g.B; row += (int64_t)gridDim.x * kWarps) {
+    const T* a = reinterpret_cast<const T*>(g.a) + row * D;
+    const T* po = reinterpret_cast<const T*>(g.po) + row * D;
+    const T* pa = reinterpret_cast<const T*>(g.pa) + row * D;
+    const T* ne = reinterpret_cast<const T*>(g.ne) + row * D;
+    Vec16<T> ra[kRegChunks], rp[kRegChunks], rq[kRegChunks], rn[kRegChunks];
+#pragma unroll
+    for (int c = 0; c < kRegChunks; ++c) {
+      const int64_t i = ((int64_t)c * 32 + lane) * VEC;
+      if (i < D) {
+        ra[c] = ld_vec16<T>(a + i);
+        rp[c] = ld_vec16<T>(po + i);
+        rq[c] = ld_vec16<T>(pa + i);
+        rn[c] = ld_vec16<T>(ne + i);
+      }
+    }
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < kRegChunks; ++c) {
+      if (((int64_t)c * 32 + lane) * VEC < D) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float va = to_f32<T>(ra[c].v[j]), vp = to_f32<T>(rp[c].v[j]);
+          const float vq = to_f32<T>(rq[c].v[j]), vn = to_f32<T>(rn[c].v[j]);
+          acc[0] = acc_term<PM>(acc[0], va - vp + eps, p);
+          acc[1] = acc_term<PM>(acc[1], va - vq + eps, p);
+          acc[2] = acc_term<PM>(acc[2], va - vn + eps, p);
+          if (swap) {
+            acc[3] = acc_term<PM>(acc[3], vp - vn + eps, p);
+            acc[4] = acc_term<PM>(acc[4], vq - vn + eps, p);
+            acc[5] = acc_term<PM>(acc[5], vp - vq + eps, p);
+          }
+        }
+      }
+    }
+    float d[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = (k < 3 || swap) ? acc_finish<PM>(acc_reduce<PM>(acc[k]), p) : 0.f;
+    const RowTerms t = row_terms(d, g.prm);
+    if (lane == 0 && g.reduction == QST_RED_NONE) g.loss_out[row] = t.loss;
+    block_sum += (double)t.loss;
+
+    const float up = g.upstream * inv_b;
+    float cnt[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (PM == PM_INF) {
+      float cc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kRegChunks; ++c) {
+        if (((int64_t)c * 32 + lane) * VEC < D) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float va = to_f32<T>(ra[c].v[j]), vp = to_f32<T>(rp[c].v[j]);
+            const float vq = to_f32<T>(rq[c].v[j]), vn = to_f32<T>(rn[c].v[j]);
+            cc[0] += fabsf(va - vp + eps) == d[0] ? 1.f : 0.f;
+            cc[1] += fabsf(va - vq + eps) == d[1] ? 1.f : 0.f;
+            cc[2] += fabsf(va - vn + eps) == d[2] ? 1.f : 0.f;
+            if (swap) {
+              cc[3] += fabsf(vp - vn + eps) == d[3] ? 1.f : 0.f;
+              cc[4] += fabsf(vq - vn + eps) == d[4] ? 1.f : 0.f;
+              cc[5] += fabsf(vp - vq + eps) == d[5] ? 1.f : 0.f;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cnt[k] = warp_sum(cc[k]);
+    }
+    float sc[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sc[k] = row_scale<PM>(d[k], p, cnt[k]) * (t.w[k] * up);
+    T* ga = g.ga ? reinterpret_cast<T*>(g.ga) + row * D : nullptr;
+    T* gp = g.gp ? reinterpret_cast<T*>(g.gp) + row * D : nullptr;
+    T* gq = g.gq ? reinterpret_cast<T*>(g.gq) + row * D : nullptr;
+    T* gn = g.gn ? reinterpret_cast<T*>(g.gn) + row * D : nullptr;
+#pragma unroll
+    for (int c = 0; c < kRegChunks; ++c) {
+      const int64_t i = ((int64_t)c * 32 + lane) * VEC;
+      if (i < D) {
+        Vec16<T> oa, op, oq, on;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float va = to_f32<T>(ra[c].v[j]), vp = to_f32<T>(rp[c].v[j]);
+          const float vq = to_f32<T>(rq[c].v[j]), vn = to_f32<T>(rn[c].v[j]);
+          const float f0 = phi<PM>(va - vp + eps, d[0], sc[0], p);
+          const float f1 = phi<PM>(va - vq + eps, d[1], sc[1], p);
+          const float f2 = phi<PM>(va - vn + eps, d[2], sc[2], p);
+          float f3 = 0.f, f4 = 0.f, f5 = 0.f;
+          if (swap) {
+            f3 = phi<PM>(vp - vn + eps, d[3], sc[3], p);
+            f4 = phi<PM>(vq - vn + eps, d[4], sc[4], p);
+            f5 = phi<PM>(vp - vq + eps, d[5], sc[5], p);
+          }
+          oa.v[j] = from_f32<T>(f0 + f1 + f2);
+          op.v[j] = from_f32<T>(-f0 + f3 + f5);
+          oq.v[j] = from_f32<T>(-f1 + f4 - f5);
+          on.v[j] = from_f32<T>(-f2 - f3 - f4);
+        }
+        if (ga) st_vec16<T>(ga + i, oa);
+        if (gp) st_vec16<T>(gp + i, op);
+        if (gq) st_vec16<T>(gq + i, oq);
+        if (gn) st_vec16<T>(gn + i, on);
+      }
+    }
+  }
+
+  if (g.reduction != QST_RED_NONE) {
+    __shared__ double s_part[kWarps];
+    __shared__ bool s_last;
+    if (lane == 0) s_part[warp] = block_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += s_part[w];
+      g.ws->partial[blockIdx.x] = tot;
+      __threadfence();
+      const unsigned int ticket = atomicAdd(&g.ws->counter, 1u);
+      s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+      __threadfence();
+      double acc2 = 0.0;
+      for (int i = lane; i < (int)gridDim.x; i += 32) acc2 += __ldcg(&g.ws->partial[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+      if (lane == 0) {
+        if (g.reduction == QST_RED_MEAN) acc2 /= (double)g.B;
+        g.loss_out[0] = (float)acc2;
+        g.ws->counter = 0u;
+      }
+    }
+  }
+}
+
+template <typename T>
+static void launch_fused_reg(const QuadArgs& a, int pm, int grid, cudaStream_t st) {
+  switch (pm) {
+    case PM_2: quad_fused_reg_kernel<T, PM_2><<<grid, kQuadThreads, 0, st>>>(a); break;
+    case PM_1: quad_fused_reg_kernel<T, PM_1><<<grid, kQuadThreads, 0, st>>>(a); break;
+    case PM_INF: quad_fused_reg_kernel<T, PM_INF><<<grid, kQuadThreads, 0, st>>>(a); break;
+    default: quad_fused_reg_kernel<T, PM_GEN><<<grid, kQuadThreads, 0, st>>>(a); break;
+  }
+}
+
 template <typename T, int VEC, int KIND>
 static void launch_pm(const QuadArgs& a, int pm, int grid, cudaStream_t st) {
   switch (pm) {
@@ -359,7 +524,12 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
     else if (kind == K_BWD) launch_vec<T, K_BWD>(a, pm, vec_ok, grid, st);   \
     else launch_vec<T, K_FUSED>(a, pm, vec_ok, grid, st);                    \
   } while (0)
-  if (dtype == QST_F32) QST_QUAD_LAUNCH(float);
+  const bool reg_path = kind == K_FUSED && vec_ok && a.D <= (int64_t)32 * vec * kRegChunks;
+  if (reg_path) {
+    if (dtype == QST_F32) launch_fused_reg<float>(a, pm, grid, st);
+    else if (dtype == QST_F16) launch_fused_reg<__half>(a, pm, grid, st);
+    else launch_fused_reg<__nv_bfloat16>(a, pm, grid, st);
+  } else if (dtype == QST_F32) QST_QUAD_LAUNCH(float);
   else if (dtype == QST_F16) QST_QUAD_LAUNCH(__half);
   else QST_QUAD_LAUNCH(__nv_bfloat16);
 #undef QST_QUAD_LAUNCH
