@@ -107,8 +107,9 @@ int qst_quadruplet_fwd_bwd(const void* x_anchor, const void* x_pos, const void* 
  * models/evaluators.py:545) and produces the bf16 operand of the tensor-core pass.
  *
  *   x: [n, d] of `dtype`, row stride d.
- *   out_bf16: [n, d_pad] bf16, d_pad = qst_padded_dim(d) (zero padded), rows scaled by
- *             1/max(||x||,1e-12) when normalize != 0.
+ *   out_bf16: [n, d_pad] bf16, d_pad = qst_padded_dim_for(d, mode) (zero padded), see qst_prep_mode.
+ *             euclidean_score (models/evaluators.py:392-405) ranks like 2q.c - ||c||^2, which the
+ *             two euclid modes turn into a plain dot product of augmented rows.
  *   out_inv_norm[n]: 1/max(||x||_2, 1e-12)            (NULL to skip)
  *   out_sq_norm[n] : ||x||_2^2                        (NULL to skip; euclid score)
  *   out_err[n]     : || bf16(row) - row_used ||_2     (NULL to skip; rounding residual used by
@@ -117,8 +118,16 @@ int qst_quadruplet_fwd_bwd(const void* x_anchor, const void* x_pos, const void* 
  *                    stats[0] = max over rows of out_err, stats[1] = max over rows of ||row_used||
  *                    (NULL to skip)
  * ------------------------------------------------------------------------------------------ */
+/* prep modes: how a row becomes a tensor-core operand */
+enum qst_prep_mode {
+  QST_PREP_RAW = 0,           /* dot_score: bf16(x) */
+  QST_PREP_COS = 1,           /* cos_sim: bf16(x / max(||x||, 1e-12)) */
+  QST_PREP_EUCLID_CORPUS = 2, /* euclid_score corpus: bf16(x) and ||x||^2 split exactly over 3 extra columns */
+  QST_PREP_EUCLID_QUERY = 3   /* euclid_score query: bf16(2x) and -1 in those columns: dot = 2q.c - ||c||^2 */
+};
 int64_t qst_padded_dim(int64_t d);
-int qst_prep_rows(const void* x, int dtype, int64_t n, int64_t d, int normalize, void* out_bf16,
+int64_t qst_padded_dim_for(int64_t d, int mode);
+int qst_prep_rows(const void* x, int dtype, int64_t n, int64_t d, int mode, void* out_bf16,
                   float* out_inv_norm, float* out_sq_norm, float* out_err, float* stats,
                   qst_stream_t stream);
 

@@ -1,0 +1,64 @@
+"""Probe for config 2: what does a plain 50 MB -> 50 MB device copy of rotating buffers cost per
+launch (the practical HBM floor for a 100 MB kernel), next to the fused loss kernel."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qst_b200  # noqa: E402
+from qst_b200 import _lib, quad_loss  # noqa: E402
+
+dev = torch.device("cuda:0")
+B, D, sets = 4096, 768, 12
+lib = _lib.load()
+g = torch.Generator(device=dev).manual_seed(1)
+data = [[torch.randn(B, D, generator=g, device=dev) for _ in range(4)] for _ in range(sets)]
+grads = [[torch.empty(B, D, device=dev) for _ in range(4)] for _ in range(sets)]
+src = [torch.randn(4 * B * D, generator=g, device=dev) for _ in range(sets)]
+dst = [torch.empty(4 * B * D, device=dev) for _ in range(sets)]
+loss = torch.empty(sets, device=dev)
+ws = torch.zeros(lib.qst_quadruplet_workspace_bytes(), dtype=torch.uint8, device=dev)
+prm = quad_loss._params(0.6, 1.0, 0.5, 0.5, 2.0, False)
+
+
+def fused(st, red):
+    for i in range(sets):
+        x, gr = data[i], grads[i]
+        _lib.check(lib.qst_quadruplet_fwd_bwd(x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), x[3].data_ptr(),
+                                              _lib.QST_F32, B, D, C.byref(prm), red, 1.0, loss[i:].data_ptr(),
+                                              gr[0].data_ptr(), gr[1].data_ptr(), gr[2].data_ptr(),
+                                              gr[3].data_ptr(), ws.data_ptr(), st))
+
+
+def copies(st):
+    for i in range(sets):
+        dst[i].copy_(src[i])
+
+
+def timeit(name, fn):
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        fn(side.cuda_stream)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fn(torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / (20 * sets)
+    print(f"{name:34s} {us:7.2f} us/launch  {8 * B * D * 4 / us / 1e3:7.0f} GB/s")
+
+
+timeit("torch copy 50MB->50MB", copies)
+timeit("fused loss mean (reg path)", lambda st: fused(st, _lib.QST_RED_MEAN))
+timeit("fused loss none (no reduction)", lambda st: fused(st, _lib.QST_RED_NONE))

@@ -12,7 +12,8 @@ Public surface (same names and call signatures as the reference side uses):
 * ``GammaQuadrupletLoss``, ``QuadrupletLoss``, ``gamma_quadruplet_loss``
   (``/root/reference/models/losses/losses.py``)
 * ``InformationRetrievalEvaluator``, ``cos_sim``, ``dot_score``
-  (sentence-transformers 2.2.2, as constructed at ``ir_evauation_script.py:107-123``)
+  (sentence-transformers 2.2.2, as constructed at ``ir_evauation_script.py:107-123``) and the
+  reference's own ``euclidean_score`` (``models/evaluators.py:392-405``)
 * ``CorpusIndex``, ``topk``: the scoring engine underneath
 * ``ShardedCorpus``: corpus-sharded retrieval over NCCL
 
@@ -22,13 +23,14 @@ from . import _lib
 from ._lib import QstError, QstLibraryError
 from .quad_loss import (GammaQuadrupletLoss, QuadrupletLoss, gamma_quadruplet_loss,
                         gamma_quadruplet_loss_and_grads)
-from .scoring import CorpusIndex, TopkResult, cos_sim, dot_score, prepare_rows, topk, topk_host
+from .scoring import (CorpusIndex, TopkResult, cos_sim, dot_score, euclidean_score, prepare_rows, topk,
+                      topk_host)
 from .ir_evaluator import InformationRetrievalEvaluator
 from . import metrics, synth
 from .sharded import ShardedCorpus
 
 __all__ = [
     "GammaQuadrupletLoss", "QuadrupletLoss", "gamma_quadruplet_loss", "gamma_quadruplet_loss_and_grads",
-    "InformationRetrievalEvaluator", "cos_sim", "dot_score", "CorpusIndex", "TopkResult", "topk",
+    "InformationRetrievalEvaluator", "cos_sim", "dot_score", "euclidean_score", "CorpusIndex", "TopkResult", "topk",
     "topk_host", "prepare_rows", "ShardedCorpus", "metrics", "synth", "QstError", "QstLibraryError",
 ]

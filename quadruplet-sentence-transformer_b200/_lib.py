@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libqst.so")
 QST_F32, QST_F16, QST_BF16 = 0, 1, 2
 QST_RED_NONE, QST_RED_SUM, QST_RED_MEAN = 0, 1, 2
 QST_SCORE_COS, QST_SCORE_DOT, QST_SCORE_EUCLID = 0, 1, 2
+QST_PREP_RAW, QST_PREP_COS, QST_PREP_EUCLID_CORPUS, QST_PREP_EUCLID_QUERY = 0, 1, 2, 3
 QST_QUAD_SAVED_PER_ROW = 8
 
 REDUCTION_CODES = {"none": QST_RED_NONE, "sum": QST_RED_SUM, "mean": QST_RED_MEAN}
@@ -61,6 +62,7 @@ SIGNATURES = {
     "qst_quadruplet_fwd_bwd": (_INT, [_P, _P, _P, _P, _INT, _I64, _I64, C.POINTER(QuadParams), _INT, C.c_float,
                                        _P, _P, _P, _P, _P, _P, _P]),
     "qst_padded_dim": (_I64, [_I64]),
+    "qst_padded_dim_for": (_I64, [_I64, _INT]),
     "qst_prep_rows": (_INT, [_P, _INT, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "qst_topk_plan_make": (_INT, [_I64, _I64, _I64, _INT, _INT, _INT, _INT, C.POINTER(TopkPlan)]),
     "qst_score_select": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P]),

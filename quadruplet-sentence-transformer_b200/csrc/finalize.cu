@@ -105,6 +105,14 @@ __device__ void block_bitonic_sort(float* sc, int32_t* ix, int n2) {
 
 // Exact fp32 dot product of a shared-memory query row with a global corpus row, one warp.
 // Both K3 (rescoring) and the exact re-scan call this, so a row gets bit-identical scores in both.
+// SQ = true accumulates (q_i - c_i)^2 instead of q_i * c_i (euclidean_score).
+template <bool SQ>
+__device__ __forceinline__ float acc1(float a, float c, float acc) {
+  if (SQ) { const float d = a - c; return fmaf(d, d, acc); }
+  return fmaf(a, c, acc);
+}
+
+template <bool SQ>
 __device__ __forceinline__ float warp_dot_f32(const float* __restrict__ qrow, const float* __restrict__ crow, int D,
                                               bool vec4, int lane) {
   float acc = 0.f;
@@ -114,17 +122,18 @@ __device__ __forceinline__ float warp_dot_f32(const float* __restrict__ qrow, co
     for (int i = lane; i < D / 4; i += 32) {
       const float4 c = __ldg(c4 + i);
       const float4 a = q4[i];
-      acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc);
-      acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+      acc = acc1<SQ>(a.x, c.x, acc); acc = acc1<SQ>(a.y, c.y, acc);
+      acc = acc1<SQ>(a.z, c.z, acc); acc = acc1<SQ>(a.w, c.w, acc);
     }
   } else {
-    for (int i = lane; i < D; i += 32) acc = fmaf(qrow[i], __ldg(crow + i), acc);
+    for (int i = lane; i < D; i += 32) acc = acc1<SQ>(qrow[i], __ldg(crow + i), acc);
   }
   return warp_sum(acc);
 }
 
 // Two rows at once: same per-row operation order as warp_dot_f32 (bit-identical results), twice the
 // loads in flight.
+template <bool SQ>
 __device__ __forceinline__ void warp_dot_f32_x2(const float* __restrict__ qrow, const float* __restrict__ c0,
                                                 const float* __restrict__ c1, int D, bool vec4, int lane, float& o0,
                                                 float& o1) {
@@ -137,14 +146,14 @@ __device__ __forceinline__ void warp_dot_f32_x2(const float* __restrict__ qrow, 
       const float4 x = __ldg(p0 + i);
       const float4 y = __ldg(p1 + i);
       const float4 a = q4[i];
-      a0 = fmaf(a.x, x.x, a0); a0 = fmaf(a.y, x.y, a0); a0 = fmaf(a.z, x.z, a0); a0 = fmaf(a.w, x.w, a0);
-      a1 = fmaf(a.x, y.x, a1); a1 = fmaf(a.y, y.y, a1); a1 = fmaf(a.z, y.z, a1); a1 = fmaf(a.w, y.w, a1);
+      a0 = acc1<SQ>(a.x, x.x, a0); a0 = acc1<SQ>(a.y, x.y, a0); a0 = acc1<SQ>(a.z, x.z, a0); a0 = acc1<SQ>(a.w, x.w, a0);
+      a1 = acc1<SQ>(a.x, y.x, a1); a1 = acc1<SQ>(a.y, y.y, a1); a1 = acc1<SQ>(a.z, y.z, a1); a1 = acc1<SQ>(a.w, y.w, a1);
     }
   } else {
     for (int i = lane; i < D; i += 32) {
       const float a = qrow[i];
-      a0 = fmaf(a, __ldg(c0 + i), a0);
-      a1 = fmaf(a, __ldg(c1 + i), a1);
+      a0 = acc1<SQ>(a, __ldg(c0 + i), a0);
+      a1 = acc1<SQ>(a, __ldg(c1 + i), a1);
     }
   }
   o0 = warp_sum(a0);
@@ -152,6 +161,7 @@ __device__ __forceinline__ void warp_dot_f32_x2(const float* __restrict__ qrow, 
 }
 
 __device__ __forceinline__ float apply_score(float dot, int score, float q_inv, const float* c_inv, int row) {
+  if (score == QST_SCORE_EUCLID) return 1.0f / (1.0f + sqrtf(dot));   // `dot` is ||q-c||^2 here
   return score == QST_SCORE_COS ? (dot * q_inv) * (c_inv ? c_inv[row] : 1.0f) : dot;
 }
 
@@ -272,19 +282,23 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   __syncthreads();
   const float qi = (P.score == QST_SCORE_COS && P.q_inv) ? P.q_inv[q] : 1.0f;
   const bool vec4 = (P.D % 4) == 0 && ((reinterpret_cast<uintptr_t>(P.c_f32) & 15u) == 0);
+  const bool sq = P.score == QST_SCORE_EUCLID;
   for (int j = warp; j < ncand; j += 2 * kFinWarps) {
     const int j1 = j + kFinWarps;
     const int c0 = idx[j];
+    const float* r0 = P.c_f32 + (size_t)c0 * P.D;
     if (j1 < ncand) {
       const int c1 = idx[j1];
+      const float* r1 = P.c_f32 + (size_t)c1 * P.D;
       float d0, d1;
-      warp_dot_f32_x2(qrow, P.c_f32 + (size_t)c0 * P.D, P.c_f32 + (size_t)c1 * P.D, P.D, vec4, lane, d0, d1);
+      if (sq) warp_dot_f32_x2<true>(qrow, r0, r1, P.D, vec4, lane, d0, d1);
+      else warp_dot_f32_x2<false>(qrow, r0, r1, P.D, vec4, lane, d0, d1);
       if (lane == 0) {
         exact[j] = apply_score(d0, P.score, qi, P.c_inv, c0);
         exact[j1] = apply_score(d1, P.score, qi, P.c_inv, c1);
       }
     } else {
-      const float d0 = warp_dot_f32(qrow, P.c_f32 + (size_t)c0 * P.D, P.D, vec4, lane);
+      const float d0 = sq ? warp_dot_f32<true>(qrow, r0, P.D, vec4, lane) : warp_dot_f32<false>(qrow, r0, P.D, vec4, lane);
       if (lane == 0) exact[j] = apply_score(d0, P.score, qi, P.c_inv, c0);
     }
   }
@@ -302,21 +316,32 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
     P.out_val[(size_t)q * kk + j] = ok ? exact[j] : -INFINITY;
     P.out_idx[(size_t)q * kk + j] = ok ? (int64_t)idx[j] + P.idx_offset : (int64_t)-1;
   }
-  if (P.out_margin && tid == 0) {
-    float margin = INFINITY;
-    if (ncand >= kk && t_bf > -INFINITY) {
-      // rigorous bound on |bf16 tensor-core score - exact score| for this query against any row:
-      //   |dq.c| + |q.dc| + |dq.dc| <= eq*cn + qn*ec + eq*ec      (Cauchy-Schwarz)
-      //   + fp32 accumulation inside the tensor core: <= D * 2^-23 * qn * cn
-      float eps = 0.f;
-      if (P.q_err && P.c_stats) {
-        const float eq = P.q_err[q], ec = P.c_stats[0], cn = P.c_stats[1];
-        const float qn = P.score == QST_SCORE_COS ? (qnorm2 > 0.f ? 1.0f : 0.f) : sqrtf(qnorm2);
-        eps = eq * cn + qn * ec + eq * ec + (float)P.D * 1.2e-7f * qn * cn;
-      }
-      margin = exact[kk - 1] - (t_bf + eps);
+  if (P.out_margin) {
+    // euclid: the tensor-core keys live in "2 q.c - ||c||^2" space; bring the k-th best back there
+    float kth = ncand >= kk ? exact[kk - 1] : 0.f;
+    if (sq && ncand >= kk && warp == 0) {
+      const float d2 = warp_dot_f32<true>(qrow, P.c_f32 + (size_t)idx[kk - 1] * P.D, P.D, vec4, lane);
+      kth = qnorm2 - d2;
     }
-    P.out_margin[q] = margin;
+    if (tid == 0) {
+      float margin = INFINITY;
+      if (ncand >= kk && t_bf > -INFINITY) {
+        // rigorous bound on |bf16 tensor-core score - exact score| for this query against any row:
+        //   |dq.c| + |q.dc| + |dq.dc| <= eq*cn + qn*ec + eq*ec      (Cauchy-Schwarz)
+        //   + fp32 accumulation inside the tensor core: <= D * 2^-23 * (sum of |terms|)
+        float eps = 0.f;
+        if (P.q_err && P.c_stats) {
+          const float eq = P.q_err[q], ec = P.c_stats[0], cn = P.c_stats[1];
+          float qn = sqrtf(qnorm2);
+          if (P.score == QST_SCORE_COS) qn = qnorm2 > 0.f ? 1.0f : 0.f;
+          if (sq) qn *= 2.0f;   // the query operand is 2q
+          eps = eq * cn + qn * ec + eq * ec + (float)P.D * 1.2e-7f * (qn * cn + (sq ? cn * cn : 0.f));
+          if (sq) eps += 1e-5f * cn * cn;   // fp32 evaluation of ||c||^2 and of the exact distance
+        }
+        margin = kth - (t_bf + eps);
+      }
+      P.out_margin[q] = margin;
+    }
   }
 }
 
@@ -402,6 +427,7 @@ __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k
   const int nf = hdr->n_flagged;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool vec4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(c_f32) & 15u) == 0);
+  const bool sq = score == QST_SCORE_EUCLID;
   for (int f0 = 0; f0 < nf; f0 += kRescanBatch) {
     const int nb = min(kRescanBatch, nf - f0);
     __syncthreads();
@@ -429,15 +455,21 @@ __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k
 #pragma unroll
           for (int b = 0; b < kRescanBatch; ++b) {
             const float4 a = reinterpret_cast<const float4*>(s_q + (size_t)b * D)[i];
-            acc[b] = fmaf(a.x, c.x, acc[b]); acc[b] = fmaf(a.y, c.y, acc[b]);
-            acc[b] = fmaf(a.z, c.z, acc[b]); acc[b] = fmaf(a.w, c.w, acc[b]);
+            if (sq) {
+              acc[b] = acc1<true>(a.x, c.x, acc[b]); acc[b] = acc1<true>(a.y, c.y, acc[b]);
+              acc[b] = acc1<true>(a.z, c.z, acc[b]); acc[b] = acc1<true>(a.w, c.w, acc[b]);
+            } else {
+              acc[b] = acc1<false>(a.x, c.x, acc[b]); acc[b] = acc1<false>(a.y, c.y, acc[b]);
+              acc[b] = acc1<false>(a.z, c.z, acc[b]); acc[b] = acc1<false>(a.w, c.w, acc[b]);
+            }
           }
         }
       } else {
         for (int i = lane; i < D; i += 32) {
           const float c = __ldg(crow + i);
 #pragma unroll
-          for (int b = 0; b < kRescanBatch; ++b) acc[b] = fmaf(s_q[(size_t)b * D + i], c, acc[b]);
+          for (int b = 0; b < kRescanBatch; ++b)
+            acc[b] = sq ? acc1<true>(s_q[(size_t)b * D + i], c, acc[b]) : acc1<false>(s_q[(size_t)b * D + i], c, acc[b]);
         }
       }
 #pragma unroll
@@ -545,7 +577,7 @@ extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int scor
                                 float* out_val, int64_t* out_idx, float* margin_inout, void* scratch,
                                 qst_stream_t stream) {
   QST_CHECK_ARG(q_f32 && c_f32 && out_val && out_idx && margin_inout && scratch, "exact_rescan: null argument");
-  QST_CHECK_ARG(score == QST_SCORE_COS || score == QST_SCORE_DOT, "exact_rescan: unsupported score %d", score);
+  QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "exact_rescan: unknown score %d", score);
   QST_CHECK_ARG((size_t)kRescanBatch * D * 4 <= 200 * 1024, "exact_rescan: D too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* p = reinterpret_cast<uint8_t*>(scratch);

@@ -630,7 +630,7 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
                 (long long)D);
   QST_CHECK_ARG(Q < (1ll << 31) - BM && N < (1ll << 31) - BN, "plan_make: Q and N must fit in int32");
   QST_CHECK_ARG(k >= 1 && k <= 1024, "plan_make: k must be in [1, 1024], %d given", k);
-  QST_CHECK_ARG(score == QST_SCORE_COS || score == QST_SCORE_DOT, "plan_make: score %d not supported by the tensor-core path", score);
+  QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "plan_make: unknown score function %d", score);
   if (sm_count <= 0) sm_count = device_sm_count();
   if (sm_count <= 0) sm_count = 148;
   if (kprime <= 0) {
@@ -642,7 +642,7 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   kprime = (int)round_up(kprime, 32);
   QST_CHECK_ARG(kprime >= k && kprime <= 2048, "plan_make: kprime %d out of range [k, 2048]", kprime);
   memset(plan, 0, sizeof(*plan));
-  plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim(D);
+  plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim_for(D, score == QST_SCORE_EUCLID ? QST_PREP_EUCLID_CORPUS : QST_PREP_RAW);
   plan->k = k; plan->kprime = kprime;
   plan->score = score;
   plan->ctas = default_ctas();

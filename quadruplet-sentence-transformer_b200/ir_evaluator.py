@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib, metrics, scoring
-from .scoring import cos_sim, dot_score
+from .scoring import cos_sim, dot_score, euclidean_score
 
 logger = logging.getLogger(__name__)
 
@@ -54,7 +54,7 @@ class InformationRetrievalEvaluator:
             if scoring.score_name_of(fn) is None:
                 raise TypeError(
                     f"score function {fn_name!r} is not one of this package's fused score functions "
-                    f"(cos_sim, dot_score); arbitrary callables would need the dense [Q, N] matrix this "
+                    f"(cos_sim, dot_score, euclidean_score); arbitrary callables would need the dense [Q, N] matrix this "
                     f"implementation never builds")
         self.queries_ids = [qid for qid in queries if qid in relevant_docs and len(relevant_docs[qid]) > 0]
         self.queries = [queries[qid] for qid in self.queries_ids]
@@ -175,7 +175,7 @@ class InformationRetrievalEvaluator:
                 for fn_name, fn in self.score_functions.items():
                     score = scoring.score_name_of(fn)
                     if score not in prepared_q:
-                        prepared_q[score] = scoring.prepare_rows(q_emb, normalize=(score == "cos_sim"))
+                        prepared_q[score] = scoring.prepare_rows(q_emb, scoring.QUERY_PREP[score])
                     index = scoring.CorpusIndex(sub, score, idx_offset=start)
                     kk = min(k, end - start)
                     res = scoring.topk(None, index, kk, self.kprime, exact=True, prepared_queries=prepared_q[score])

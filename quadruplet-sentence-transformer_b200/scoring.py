@@ -18,7 +18,13 @@ import torch
 
 from . import _lib
 
-SCORE_CODES = {"cos_sim": _lib.QST_SCORE_COS, "dot_score": _lib.QST_SCORE_DOT}
+SCORE_CODES = {"cos_sim": _lib.QST_SCORE_COS, "dot_score": _lib.QST_SCORE_DOT,
+               "euclid_score": _lib.QST_SCORE_EUCLID}
+# how corpus rows / query rows become tensor-core operands for each score function (qst_prep_mode)
+CORPUS_PREP = {"cos_sim": _lib.QST_PREP_COS, "dot_score": _lib.QST_PREP_RAW,
+               "euclid_score": _lib.QST_PREP_EUCLID_CORPUS}
+QUERY_PREP = {"cos_sim": _lib.QST_PREP_COS, "dot_score": _lib.QST_PREP_RAW,
+              "euclid_score": _lib.QST_PREP_EUCLID_QUERY}
 
 
 def cos_sim(a, b):
@@ -36,8 +42,15 @@ def dot_score(a, b):
     return _dense_scores(a, b, "dot_score")
 
 
+def euclidean_score(a, b):
+    """Marker + dense entry for the reference's own score function ``1 / (1 + cdist(a, b))``
+    (``/root/reference/models/evaluators.py:392-405``, wired in at ``ir_evauation_script.py:70``)."""
+    return _dense_scores(a, b, "euclid_score")
+
+
 cos_sim.qst_score = "cos_sim"
 dot_score.qst_score = "dot_score"
+euclidean_score.qst_score = "euclid_score"
 
 
 def score_name_of(fn) -> Optional[str]:
@@ -72,8 +85,10 @@ class PreparedRows:
         return self.f32.shape[1]
 
 
-def prepare_rows(x: torch.Tensor, normalize: bool) -> PreparedRows:
-    """K1 (``qst_prep_rows``): norms, optional normalisation, bf16 cast, zero padding."""
+def prepare_rows(x: torch.Tensor, mode) -> PreparedRows:
+    """K1 (``qst_prep_rows``): norms, bf16 operand for the given ``qst_prep_mode`` (``True``/``False``
+    are accepted as cos / raw), zero padding."""
+    mode = int(mode)
     lib = _lib.load()
     x = _as_2d_cuda(x)
     if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
@@ -81,14 +96,14 @@ def prepare_rows(x: torch.Tensor, normalize: bool) -> PreparedRows:
     x = x.contiguous()
     n, d = x.shape
     dev = x.device
-    d_pad = lib.qst_padded_dim(d)
+    d_pad = lib.qst_padded_dim_for(d, mode)
     with torch.cuda.device(dev):
         bf = torch.empty((n, d_pad), dtype=torch.bfloat16, device=dev)
         inv = torch.empty(n, dtype=torch.float32, device=dev)
         sq = torch.empty(n, dtype=torch.float32, device=dev)
         err = torch.empty(n, dtype=torch.float32, device=dev)
         stats = torch.zeros(2, dtype=torch.float32, device=dev)
-        _lib.check(lib.qst_prep_rows(x.data_ptr(), _lib.dtype_code(x.dtype), n, d, int(normalize), bf.data_ptr(),
+        _lib.check(lib.qst_prep_rows(x.data_ptr(), _lib.dtype_code(x.dtype), n, d, mode, bf.data_ptr(),
                                      inv.data_ptr(), sq.data_ptr(), err.data_ptr(), stats.data_ptr(),
                                      _lib.stream_ptr(dev)))
     f32 = x if x.dtype == torch.float32 else x.float()
@@ -107,7 +122,7 @@ class CorpusIndex:
             raise ValueError(f"score must be one of {sorted(SCORE_CODES)}, {score} given")
         self.score = score
         self.idx_offset = int(idx_offset)
-        self.rows = prepare_rows(corpus_embeddings, normalize=(score == "cos_sim"))
+        self.rows = prepare_rows(corpus_embeddings, CORPUS_PREP[score])
 
     @property
     def n(self) -> int:
@@ -157,7 +172,7 @@ def topk(queries: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0, exa
     ``exact=True`` queries whose certificate fails are re-scanned in fp32 on the device.
     """
     lib = _lib.load()
-    pq = prepared_queries if prepared_queries is not None else prepare_rows(queries, index.score == "cos_sim")
+    pq = prepared_queries if prepared_queries is not None else prepare_rows(queries, QUERY_PREP[index.score])
     if pq.d != index.d:
         raise ValueError(f"query dim {pq.d} != corpus dim {index.d}")
     dev = index.device

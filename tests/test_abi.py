@@ -43,8 +43,10 @@ def test_version_and_error_channel(lib):
     assert rc == -1 and b"bad shape" in lib.qst_last_error()
     rc = lib.qst_topk_plan_make(10, 10, 8, 5000, 0, 0, 148, C.byref(plan))
     assert rc == -1 and b"k must be" in lib.qst_last_error()
-    rc = lib.qst_topk_plan_make(10, 10, 8, 5, 0, 2, 148, C.byref(plan))      # euclid: not on this path yet
+    rc = lib.qst_topk_plan_make(10, 10, 8, 5, 0, 3, 148, C.byref(plan))      # unknown score function
     assert rc == -1
+    assert lib.qst_topk_plan_make(10, 10, 8, 5, 0, 2, 148, C.byref(plan)) == 0 and plan.D_pad == 64
+    assert lib.qst_padded_dim_for(768, 2) == 832 and lib.qst_padded_dim_for(768, 1) == 768
 
 
 def test_plan_invariants(lib):

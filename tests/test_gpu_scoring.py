@@ -53,8 +53,8 @@ def test_tensorcore_scores_match_bf16_matmul(Q, N, D, ctas):
     g = torch.Generator().manual_seed(14)
     q = torch.randn(Q, D, generator=g)
     c = torch.randn(N, D, generator=g)
-    pq = scoring.prepare_rows(q.to(_dev()), normalize=True)
-    pc = scoring.prepare_rows(c.to(_dev()), normalize=True)
+    pq = scoring.prepare_rows(q.to(_dev()), True)
+    pc = scoring.prepare_rows(c.to(_dev()), True)
     # K1 against torch
     qn = torch.nn.functional.normalize(q, p=2, dim=1)
     assert pq.bf16.shape[1] % 64 == 0
@@ -77,7 +77,7 @@ def _oracle_topk(q, c, k, score="cos_sim", chunk=50000):
 
 @pytest.mark.parametrize("Q,N,D,k", [(1000, 10000, 384, 10), (64, 3000, 768, 100), (200, 20000, 96, 100),
                                      (5, 40, 16, 10), (130, 257, 33, 7)])
-@pytest.mark.parametrize("score", ["cos_sim", "dot_score"])
+@pytest.mark.parametrize("score", ["cos_sim", "dot_score", "euclid_score"])
 def test_topk_matches_oracle(Q, N, D, k, score, ctas):
     import qst_b200
     g = torch.Generator().manual_seed(14 + Q)
@@ -339,3 +339,39 @@ def test_metrics_at_scale_match_reference_loops():
     for metric in want:
         for k, v in want[metric].items():
             assert float(got[metric][k]) == float(v), (metric, k, got[metric][k], v)
+
+
+def test_euclidean_score_operands_and_script_default_score_set():
+    """euclidean_score (models/evaluators.py:392-405) on the tensor-core path: the augmented bf16
+    operands reproduce 2 q.c - ||c||^2, and the evaluator runs the script's default score set
+    ('all' = cos_sim, dot_score, euclid_score, ir_evauation_script.py:70,179-183)."""
+    import qst_b200
+    from qst_b200 import scoring, _lib
+    from oracle import ir_oracle
+    g = torch.Generator().manual_seed(21)
+    q = torch.randn(40, 100, generator=g) * 2.0
+    c = torch.randn(900, 100, generator=g) * (0.5 + torch.rand(900, 1, generator=g))
+    pq = scoring.prepare_rows(q.to(_dev()), _lib.QST_PREP_EUCLID_QUERY)
+    pc = scoring.prepare_rows(c.to(_dev()), _lib.QST_PREP_EUCLID_CORPUS)
+    assert pq.bf16.shape[1] == 128 and pc.bf16.shape[1] == 128          # 100 + 3 -> 128
+    keys = scoring.dense_tensorcore_scores(pq.bf16, pc.bf16).cpu()
+    want = 2 * (q.bfloat16().float() @ c.bfloat16().float().T) - (c * c).sum(1)[None, :]
+    torch.testing.assert_close(keys, want, rtol=0, atol=2e-3 * float(want.abs().max()) / 100)
+    dense = qst_b200.euclidean_score(q.to(_dev()), c.to(_dev()))
+    torch.testing.assert_close(dense.cpu(), ir_oracle.euclidean_score(q, c), rtol=0, atol=2e-6)
+    # evaluator with the three score functions of the reference script
+    qq, cc, queries, corpus, relevant = qst_b200.synth.ir_eval_set(200, 3000, 64)
+    table = torch.cat([qq, cc])
+    kw = dict(mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1, 3, 5, 10], precision_recall_at_k=[1, 3, 5, 10],
+              map_at_k=[100], write_csv=False)
+    ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
+        "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score}, **kw)
+    ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, score_functions={
+        "cos_sim": ir_oracle.cos_sim, "dot_score": ir_oracle.dot_score, "euclid_score": ir_oracle.euclidean_score}, **kw)
+    got = ev.compute_metrices(qst_b200.synth.TableModel(table.to(_dev())))
+    want_m = ref.compute_metrices(ir_oracle.PrecomputedEmbeddingModel(table))
+    for fn in want_m:
+        for metric in want_m[fn]:
+            for k, v in want_m[fn][metric].items():
+                assert float(got[fn][metric][k]) == float(v), (fn, metric, k, got[fn][metric][k], v)
+    assert all(bool((m > 0).all()) for m in ev.last_margins.values())
