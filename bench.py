@@ -6,8 +6,9 @@ corpus, top-100), one JSON line on stdout.
 
 A *step* is one pass of the hot path over one batch of synthetic queries: K1 on the queries,
 K2 tensor-core scoring + streaming top-k', K3 fp32 rescoring/ordering (+ the exact re-scan kernels,
-which find nothing to do when every query is certified) and, for N > 1, the NCCL all-gather of the
-per-shard lists and the on-device merge.
+which find nothing to do when every query is certified).  For N > 1 every shard lists its best
+candidates per query by bf16 key, ONE NCCL all-to-all routes the lists to the rank owning each query,
+which rescoring-finalises them, and an all-gather distributes the rankings.
 
 Workload (config 3 of BASELINE.json): 10 000 queries x 1 000 000 corpus rows x 768-d, fp32 masters
 -> bf16 tensor-core operands, k = 100.  For N > 1 the 1M-row corpus is sharded over the N GPUs
@@ -281,29 +282,24 @@ def run_ours(args):
     Q = Q_PER_GPU * world
     n0, n1 = sharded.shard_bounds(N_CORPUS, world, rank)
     gen = torch.Generator(device=dev).manual_seed(14 + 100)
-    corpus_full_rows = []
-    # every rank draws the same global corpus stream and keeps its own rows, so the union over
-    # ranks is the same 1M-row corpus whatever N is
+    # every rank draws the same global corpus stream, so the corpus is the same 1M rows whatever N
+    # is; for N > 1 the full fp32 master stays resident on every rank (3 GB, rescoring only) while
+    # the bf16 tensor-core operand is built for this rank's rows only
     slab = 125_000
-    for s in range(0, N_CORPUS, slab):
-        x = torch.randn(slab, DIM, generator=gen, device=dev, dtype=torch.float32)
-        lo, hi = max(s, n0), min(s + slab, n1)
-        if lo < hi:
-            corpus_full_rows.append(x[lo - s:hi - s].clone())
-        del x
-    shard = torch.cat(corpus_full_rows)
-    del corpus_full_rows
+    full = torch.cat([torch.randn(slab, DIM, generator=gen, device=dev, dtype=torch.float32)
+                      for _ in range(N_CORPUS // slab)])
+    shard = full[n0:n1]
     qgen = torch.Generator(device=dev).manual_seed(14 + 200)
     queries = torch.randn(Q, DIM, generator=qgen, device=dev, dtype=torch.float32)
     queries_host = queries.cpu().pin_memory()
 
     if world > 1:
-        corp = sharded.ShardedCorpus(shard, N_CORPUS, "cos_sim", query_tile=Q_PER_GPU * 2)
+        corp = sharded.ShardedCorpus(shard, N_CORPUS, "cos_sim", full_master=full)
         index = corp.index
     else:
         corp = None
         index = qst_b200.CorpusIndex(shard, "cos_sim", idx_offset=0)
-    del shard
+    del shard, full
     torch.cuda.synchronize()
 
     def step_device():
@@ -403,15 +399,16 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"cos_sim + top-{TOPK}: {Q} queries x {N_CORPUS} corpus x {DIM}-d, fp32 masters, "
-                               f"bf16 tensor-core first pass k'={plan.kprime}, fp32 rescore; corpus sharded over "
-                               f"{world} GPU(s), {Q_PER_GPU} queries per GPU per step",
+                               f"bf16 tensor-core first pass k'={plan.kprime}, fp32 rescore; bf16 operand sharded over "
+                               f"{world} GPU(s) (fp32 master replicated for N>1), {Q_PER_GPU} queries per GPU per step",
                    "l2": "inputs larger than L2 (bf16 corpus shard %.2f GB + fp32 masters)" % (index.n * DIM * 2 / 1e9),
                    "plan": {"m_tiles": plan.m_tiles, "n_tiles": plan.n_tiles, "stripes": plan.stripes,
                             "units": plan.units, "grid": plan.grid},
                    "uncertified_queries_after_first_pass_and_rescan": uncertified},
         "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-        "gpu_launches": steps * (6 + (1 if world > 1 else 0)),
+        # K1, K2, K3 (+ list unpack / select for N > 1), 3 re-scan kernels
+        "gpu_launches": steps * (6 if world == 1 else 8),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic, "kernel": "score_select_kernel",
                      "kernel_ms": k2, "peak_source": peaks["_source"] + " sustained bf16 (kernel timed inside the step loop)",

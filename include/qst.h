@@ -186,6 +186,23 @@ int qst_finalize_topk(const qst_topk_plan* plan, const void* workspace,
                       int64_t idx_offset, float* out_val, int64_t* out_idx, float* out_margin,
                       qst_stream_t stream);
 
+/* ---- corpus-sharded retrieval, candidate exchange ----------------------
+ * Step 1 on every shard, after qst_score_select: the m best candidates per query BY bf16 KEY, no
+ * rescoring.  out_lists [Q, m+1] of 8-byte entries (ordered-uint key, uint32 global row id =
+ * local row + idx_offset; id 0xffffffff = empty); entry m of each row is the trailer
+ * (bound key of everything the shard did NOT list, number of valid entries).
+ * Step 2, on the rank that owns a query, after the lists of all G shards have been exchanged
+ * (lists [G, Q, m+1]): select the k' best overall by key, rescore them exactly from the fp32 master
+ * (global row ids -> c_f32 must be the full corpus), order, emit top k + certificate, as
+ * qst_finalize_topk does.  scratch: qst_finalize_lists_scratch_bytes(Q, G). */
+int qst_select_candidates(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
+                          void* out_lists, qst_stream_t stream);
+size_t qst_finalize_lists_scratch_bytes(int64_t Q, int G);
+int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, int score, int64_t D, const void* lists,
+                       const float* q_f32, const float* q_inv, const float* q_err, const float* c_f32,
+                       const float* c_inv, const float* c_stats, float* out_val, int64_t* out_idx,
+                       float* out_margin, void* scratch, qst_stream_t stream);
+
 /* Exact fp32 brute-force re-scan for the queries whose certificate failed (margin <= 0):
  * every corpus row is scored in fp32 against each flagged query and rows scoring at least the
  * current k-th best are collected, which yields the exact top k regardless of bf16 error.

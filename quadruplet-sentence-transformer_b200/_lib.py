@@ -68,6 +68,10 @@ SIGNATURES = {
     "qst_score_select": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P]),
     "qst_score_dense": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
     "qst_finalize_topk": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "qst_select_candidates": (_INT, [C.POINTER(TopkPlan), _P, _INT, _I64, _P, _P]),
+    "qst_finalize_lists_scratch_bytes": (C.c_size_t, [_I64, _INT]),
+    "qst_finalize_lists": (_INT, [_I64, _INT, _INT, _INT, _INT, _INT, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P, _P]),
     "qst_exact_rescan_workspace_bytes": (C.c_size_t, [_I64, _INT]),
     "qst_exact_rescan": (_INT, [_I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "qst_merge_topk": (_INT, [_P, _P, _INT, _I64, _INT, _P, _P, _P]),

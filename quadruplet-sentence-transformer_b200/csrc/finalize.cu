@@ -178,6 +178,9 @@ struct FinParams {
   float* out_val;
   int64_t* out_idx;
   float* out_margin;
+  // select-only mode (sharded retrieval, step 1): write the m best candidates by bf16 key instead
+  // of rescoring; entry m of each row carries (bound key, count)
+  uint2* sel_out;
 };
 
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P) {
@@ -273,6 +276,15 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
     reduced = true;
   }
   const int ncand = fill;  // <= kprime
+  if (P.sel_out) {
+    // everything this shard did not put in the list has a bf16 key <= bound
+    const uint32_t bound = reduced ? max(T, Tstar) : Tstar;
+    uint2* dst = P.sel_out + (size_t)q * (P.kprime + 1);
+    for (int i = tid; i < P.kprime; i += kFinThreads)
+      dst[i] = i < ncand ? make_uint2(keys[i], (uint32_t)((int64_t)idx[i] + P.idx_offset)) : make_uint2(0u, 0xffffffffu);
+    if (tid == 0) dst[P.kprime] = make_uint2(bound, (uint32_t)ncand);
+    return;
+  }
   // every document that is NOT rescored below has a bf16 score <= t_bf
   const uint32_t Tmax = reduced ? max(T, Tstar) : Tstar;
   const float t_bf = key_to_float(Tmax);
@@ -522,6 +534,14 @@ __global__ void __launch_bounds__(kFinThreads) rescan_emit_kernel(int k, int64_t
   }
 }
 
+__global__ void unpack_list_trailers_kernel(const uint2* __restrict__ lists, int64_t n, int m, uint32_t* thr, int* cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 t = lists[i * (m + 1) + m];
+  thr[i] = t.x;
+  cnt[i] = (int)t.y;
+}
+
 }  // namespace qst
 
 using namespace qst;
@@ -555,6 +575,70 @@ extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspac
   QST_LAUNCH_CHECK();
   return QST_OK;
 }
+
+extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
+                                     void* out_lists, qst_stream_t stream) {
+  QST_CHECK_ARG(plan && workspace && out_lists, "select_candidates: null argument");
+  QST_CHECK_ARG(m >= 1 && m <= 2048, "select_candidates: m=%d out of range", m);
+  QST_CHECK_ARG(plan->stripes <= kMaxStripes, "select_candidates: too many stripes (%d)", plan->stripes);
+  const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
+  FinParams P{};
+  P.Q = (int)plan->Q; P.N = (int)plan->N; P.D = 0;
+  P.k = m; P.kprime = m; P.cap = plan->cap;
+  P.m_tiles = plan->m_tiles; P.stripes = plan->stripes; P.score = plan->score;
+  P.rows_per_unit = plan->rows_per_unit;
+  int sm_cap = m + plan->cap;
+  if (sm_cap < 4096) sm_cap = 4096;
+  P.sm_cap = sm_cap;
+  P.thr_hint = reinterpret_cast<const uint32_t*>(ws + plan->off_thr);
+  P.unit_cnt = reinterpret_cast<const int*>(ws + plan->off_cnt);
+  P.unit_thr = reinterpret_cast<const uint32_t*>(ws + plan->off_uthr);
+  P.unit_cand = reinterpret_cast<const uint2*>(ws + plan->off_cand);
+  P.idx_offset = idx_offset;
+  P.sel_out = reinterpret_cast<uint2*>(out_lists);
+  const size_t smem = (size_t)sm_cap * 8 + (size_t)m * 8 + 16;
+  QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<<<(unsigned)plan->Q, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, int score, int64_t D,
+                                  const void* lists, const float* q_f32, const float* q_inv, const float* q_err,
+                                  const float* c_f32, const float* c_inv, const float* c_stats, float* out_val,
+                                  int64_t* out_idx, float* out_margin, void* scratch, qst_stream_t stream) {
+  QST_CHECK_ARG(lists && q_f32 && c_f32 && out_val && out_idx && scratch, "finalize_lists: null argument");
+  QST_CHECK_ARG(Q >= 1 && G >= 1 && G <= kMaxStripes && m >= 1 && k >= 1 && kprime >= k && kprime <= 2048,
+                "finalize_lists: bad shape Q=%lld G=%d m=%d k=%d kprime=%d", (long long)Q, G, m, k, kprime);
+  QST_CHECK_ARG(score != QST_SCORE_COS || (q_inv && c_inv), "finalize_lists: cos score needs inverse norms");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // unpack the (bound, count) trailer of every received list into the arrays K3 reads
+  uint32_t* thr = reinterpret_cast<uint32_t*>(scratch);
+  int* cnt = reinterpret_cast<int*>(thr + (size_t)G * Q);
+  unpack_list_trailers_kernel<<<(unsigned)ceil_div((int64_t)G * Q, 256), 256, 0, st>>>(
+      reinterpret_cast<const uint2*>(lists), (int64_t)G * Q, m, thr, cnt);
+  QST_LAUNCH_CHECK();
+  FinParams P{};
+  P.Q = (int)Q; P.N = 0; P.D = (int)D;
+  P.k = k; P.kprime = kprime; P.cap = m + 1;          // row pitch of a received list
+  P.m_tiles = 1; P.stripes = G; P.score = score; P.rows_per_unit = (int)Q;
+  int sm_cap = kprime + m + 1;
+  if (sm_cap < G * m) sm_cap = G * m;                  // gather everything in one pass when it fits
+  if (sm_cap < 4096) sm_cap = 4096;
+  if (sm_cap > 16384) sm_cap = 16384;
+  P.sm_cap = sm_cap;
+  P.unit_cnt = cnt; P.unit_thr = thr; P.unit_cand = reinterpret_cast<const uint2*>(lists);
+  P.q_f32 = q_f32; P.q_inv = q_inv; P.q_err = q_err; P.c_f32 = c_f32; P.c_inv = c_inv; P.c_stats = c_stats;
+  P.idx_offset = 0; P.out_val = out_val; P.out_idx = out_idx; P.out_margin = out_margin;
+  const size_t smem = (size_t)sm_cap * 8 + (size_t)kprime * 8 + round_up((size_t)D * 4, 16);
+  QST_CHECK_ARG(smem <= 200 * 1024, "finalize_lists: D=%lld too large", (long long)D);
+  QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<<<(unsigned)Q, kFinThreads, smem, st>>>(P);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" size_t qst_finalize_lists_scratch_bytes(int64_t Q, int G) { return (size_t)G * Q * 8; }
 
 extern "C" int qst_merge_topk(const float* vals, const int64_t* idx, int G, int64_t Q, int k, float* out_val,
                               int64_t* out_idx, qst_stream_t stream) {

@@ -85,7 +85,7 @@ class PreparedRows:
         return self.f32.shape[1]
 
 
-def prepare_rows(x: torch.Tensor, mode) -> PreparedRows:
+def prepare_rows(x: torch.Tensor, mode, want_bf16: bool = True) -> PreparedRows:
     """K1 (``qst_prep_rows``): norms, bf16 operand for the given ``qst_prep_mode`` (``True``/``False``
     are accepted as cos / raw), zero padding."""
     mode = int(mode)
@@ -98,12 +98,12 @@ def prepare_rows(x: torch.Tensor, mode) -> PreparedRows:
     dev = x.device
     d_pad = lib.qst_padded_dim_for(d, mode)
     with torch.cuda.device(dev):
-        bf = torch.empty((n, d_pad), dtype=torch.bfloat16, device=dev)
+        bf = torch.empty((n, d_pad), dtype=torch.bfloat16, device=dev) if want_bf16 else None
         inv = torch.empty(n, dtype=torch.float32, device=dev)
         sq = torch.empty(n, dtype=torch.float32, device=dev)
         err = torch.empty(n, dtype=torch.float32, device=dev)
         stats = torch.zeros(2, dtype=torch.float32, device=dev)
-        _lib.check(lib.qst_prep_rows(x.data_ptr(), _lib.dtype_code(x.dtype), n, d, mode, bf.data_ptr(),
+        _lib.check(lib.qst_prep_rows(x.data_ptr(), _lib.dtype_code(x.dtype), n, d, mode, _lib.ptr(bf),
                                      inv.data_ptr(), sq.data_ptr(), err.data_ptr(), stats.data_ptr(),
                                      _lib.stream_ptr(dev)))
     f32 = x if x.dtype == torch.float32 else x.float()

@@ -7,12 +7,25 @@ per-rank lists are exchanged with ONE all-gather per query tile over NVLink/NVSw
 the device (``qst_merge_topk``: ties -> lower global id).  The all-gather of tile t runs on a side
 stream while tile t+1 is being scored.
 
+Two exchange strategies:
+
+* ``master="sharded"`` (default when no full master is given): every rank rescoring its own k'
+  candidates exactly, one all-gather of the exact per-shard top-k lists, merge (K6).  Works for
+  corpora whose fp32 master does not fit one GPU; rescoring work grows with the number of ranks.
+* ``master="replicated"``: only the bf16 tensor-core operand is sharded; the fp32 master
+  (N*D*4 bytes, 3 GB at 1M x 768) is resident on every rank.  Each shard lists its m best
+  candidates per query by bf16 key (``qst_select_candidates``), ONE all-to-all sends every query's
+  lists to the rank that owns the query, which rescoring-finalises them (``qst_finalize_lists``) and
+  re-scans uncertified ones; an all-gather distributes the final rankings.  Rescoring work per rank
+  stays constant as ranks are added.
+
 The reference has no multi-GPU path; its only scale-out knob is the sequential corpus chunk loop
 (``corpus_chunk_size``, ``/root/reference/ir_evauation_script.py:161``), which this replaces in
 space instead of time.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional, Tuple
 
 import torch
@@ -56,15 +69,32 @@ def merge_topk(gv: torch.Tensor, gi: torch.Tensor) -> Tuple[torch.Tensor, torch.
     return ov, oi
 
 
+def candidates_per_shard(kprime: int, world: int) -> int:
+    """m of ``qst_select_candidates``: twice a shard's fair share of the k' overall candidates plus
+    slack (placement of the best documents over shards is uneven), never more than k'."""
+    m = ((2 * -(-kprime // world) + 32 + 31) // 32) * 32
+    return max(32, min(m, kprime))
+
+
+def exchange_candidate_lists(lists: torch.Tensor, group=None) -> torch.Tensor:
+    """[G*Qown, m+1, 2] int32 (rows grouped by owner rank) -> [G, Qown, m+1, 2] received from every
+    shard for the queries this rank owns.  One all-to-all; any backend."""
+    world = dist.get_world_size(group)
+    out = torch.empty_like(lists)
+    dist.all_to_all_single(out, lists.contiguous(), group=group)
+    return out.view((world, lists.shape[0] // world) + tuple(lists.shape[1:]))
+
+
 class ShardedCorpus:
     """This rank's shard of an N-row corpus + the collective top-k over all shards."""
 
     def __init__(self, shard_embeddings: torch.Tensor, n_total: int, score: str = "cos_sim", group=None,
-                 query_tile: int = 16384):
+                 query_tile: int = 16384, full_master: Optional[torch.Tensor] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = n_total
+        self.score = score
         self.start, self.end = shard_bounds(n_total, self.world, self.rank)
         if shard_embeddings.shape[0] != self.end - self.start:
             raise ValueError(f"rank {self.rank} expects rows [{self.start}, {self.end}) = {self.end - self.start} "
@@ -72,15 +102,79 @@ class ShardedCorpus:
         self.index = scoring.CorpusIndex(shard_embeddings, score, idx_offset=self.start)
         self.query_tile = query_tile
         self._side = torch.cuda.Stream(device=self.index.device) if self.world > 1 else None
+        self.master = None
+        if full_master is not None:
+            if full_master.shape[0] != n_total:
+                raise ValueError(f"full_master must have {n_total} rows, got {full_master.shape[0]}")
+            # norms / residual statistics of the whole corpus for rescoring and the certificate; the
+            # bf16 operand is NOT built for it
+            self.master = scoring.prepare_rows(full_master, scoring.CORPUS_PREP[score], want_bf16=False)
 
+    # ---------------------------------------------------------------------------------------------
     def topk(self, queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True):
-        """Global exact top-k for every query: (values [Q, k], global ids [Q, k], local margins [Q])."""
+        """Global exact top-k for every query: (values [Q, k], global ids [Q, k], margins [Q])."""
         dev = self.index.device
         queries = queries.to(dev)
-        Q = queries.shape[0]
         if self.world == 1:
             r = scoring.topk(queries, self.index, k, kprime, exact)
             return r.values, r.indices, r.margin
+        if self.master is not None:
+            return self._topk_candidate_exchange(queries, k, kprime, exact)
+        return self._topk_list_exchange(queries, k, kprime, exact)
+
+    # ---- master="replicated": lists of bf16 candidates go to the owner of each query -----------
+    def _topk_candidate_exchange(self, queries, k, kprime, exact):
+        lib = _lib.load()
+        dev = self.index.device
+        G = self.world
+        Q = queries.shape[0]
+        q_own = -(-Q // G)
+        q_pad = q_own * G
+        score = self.score
+        cos = score == "cos_sim"
+        code = scoring.SCORE_CODES[score]
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            if q_pad != Q:     # pad with copies of the last query so that every rank owns q_own rows
+                queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
+            pq = scoring.prepare_rows(queries, scoring.QUERY_PREP[score])
+            plan = scoring.make_plan(q_pad, self.index.n, self.index.d, k, kprime, score)
+            m = candidates_per_shard(plan.kprime, G)
+            ws = scoring._workspace(plan.ws_bytes, dev, "select")
+            _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+                                            ws.data_ptr(), st))
+            lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
+            _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
+            recv = exchange_candidate_lists(lists, self.group)              # [G, q_own, m+1, 2]
+            own = slice(self.rank * q_own, (self.rank + 1) * q_own)
+            vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
+            idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
+            margin = torch.empty(q_own, dtype=torch.float32, device=dev)
+            scratch = scoring._workspace(lib.qst_finalize_lists_scratch_bytes(q_own, G), dev, "lists")
+            mst = self.master
+            q_f32 = pq.f32[own]
+            q_inv = pq.inv_norm[own] if cos else None
+            q_err = pq.err[own]
+            _lib.check(lib.qst_finalize_lists(q_own, G, m, k, plan.kprime, code, self.index.d, recv.data_ptr(),
+                                              q_f32.data_ptr(), _lib.ptr(q_inv), q_err.data_ptr(),
+                                              mst.f32.data_ptr(), mst.inv_norm.data_ptr() if cos else None,
+                                              mst.stats.data_ptr(), vals.data_ptr(), idx.data_ptr(),
+                                              margin.data_ptr(), scratch.data_ptr(), st))
+            if exact:
+                rs = scoring._workspace(lib.qst_exact_rescan_workspace_bytes(q_own, k), dev, "rescan")
+                _lib.check(lib.qst_exact_rescan(q_own, self.n_total, self.index.d, k, code, q_f32.data_ptr(),
+                                                _lib.ptr(q_inv), mst.f32.data_ptr(),
+                                                mst.inv_norm.data_ptr() if cos else None, 0, vals.data_ptr(),
+                                                idx.data_ptr(), margin.data_ptr(), rs.data_ptr(), st))
+            gv, gi = all_gather_topk(vals, idx, self.group)                 # [G, q_own, k]
+            gm = torch.empty(q_pad, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gm, margin, group=self.group)
+        return gv.view(q_pad, k)[:Q], gi.view(q_pad, k)[:Q], gm[:Q]
+
+    # ---- master="sharded": exact per-shard top-k lists, all-gather, merge ---------------------------
+    def _topk_list_exchange(self, queries, k, kprime, exact):
+        dev = self.index.device
+        Q = queries.shape[0]
         main = torch.cuda.current_stream(dev)
         out_v: List[torch.Tensor] = []
         out_i: List[torch.Tensor] = []

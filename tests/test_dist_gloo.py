@@ -45,6 +45,16 @@ def _worker(rank, world, port, out_dir):
         wv, wi = ir_oracle.topk_dense(q, c, k)
         assert torch.equal(mi, wi), (rank, mi, wi)
         torch.testing.assert_close(mv, wv, rtol=0, atol=1e-6)
+        # candidate exchange: one all-to-all routes every query's list to its owner, source-rank major
+        q_own, m = 5, 3
+        lists = torch.arange(world * q_own * (m + 1) * 2, dtype=torch.int32).view(world * q_own, m + 1, 2) + 1000 * rank
+        recv = sharded.exchange_candidate_lists(lists)
+        assert recv.shape == (world, q_own, m + 1, 2)
+        for src in range(world):
+            want = (torch.arange(world * q_own * (m + 1) * 2, dtype=torch.int32).view(world * q_own, m + 1, 2)
+                    + 1000 * src)[rank * q_own:(rank + 1) * q_own]
+            assert torch.equal(recv[src], want)
+        assert sharded.candidates_per_shard(192, 8) == 96 and sharded.candidates_per_shard(192, 1) == 192
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,54 @@
+"""Real multi-GPU run of the corpus-sharded path (NCCL): both exchange strategies against the CPU
+oracle.  Needs >= 2 visible GPUs (`gpurun --gpus 2`), skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import qst_b200
+        from qst_b200 import sharded
+        from oracle import ir_oracle
+        g = torch.Generator().manual_seed(14)
+        Q, N, D, k = 333, 40_003, 128, 100
+        q = torch.randn(Q, D, generator=g)
+        c = torch.randn(N, D, generator=g)
+        want_val, want_idx = ir_oracle.topk_dense(q, c, k)
+        s, e = sharded.shard_bounds(N, world, rank)
+        for full in (None, c.to(dev)):
+            corp = sharded.ShardedCorpus(c[s:e].to(dev), N, "cos_sim", query_tile=128, full_master=full)
+            vals, idx, margin = corp.topk(q.to(dev), k)
+            torch.cuda.synchronize()
+            assert vals.shape == (Q, k) and bool((margin > 0).all())
+            torch.testing.assert_close(vals.cpu(), want_val, rtol=0, atol=2e-6)
+            mism = (idx.cpu() != want_idx)
+            # only tie swaps (scores within 1e-6) may differ
+            assert float((vals.cpu()[mism] - want_val[mism]).abs().max() if mism.any() else 0.0) <= 2e-6
+            assert mism.float().mean() < 1e-3
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_retrieval_matches_oracle(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]

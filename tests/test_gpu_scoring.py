@@ -375,3 +375,59 @@ def test_euclidean_score_operands_and_script_default_score_set():
             for k, v in want_m[fn][metric].items():
                 assert float(got[fn][metric][k]) == float(v), (fn, metric, k, got[fn][metric][k], v)
     assert all(bool((m > 0).all()) for m in ev.last_margins.values())
+
+
+def test_candidate_exchange_emulated_on_one_gpu():
+    """Sharded retrieval with candidate exchange (qst_select_candidates -> all-to-all ->
+    qst_finalize_lists), the G shards emulated on one GPU: must equal the unsharded oracle."""
+    import ctypes as C
+    import qst_b200
+    from qst_b200 import scoring, sharded, _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(8)
+    Q, N, D, k, G = 150, 30011, 96, 50, 4
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g) * (1 + torch.rand(N, 1, generator=g))
+    dev = _dev()
+    for score in ("cos_sim", "dot_score", "euclid_score"):
+        want_val, want_idx = _oracle_topk(q, c, k, score)
+        pq = scoring.prepare_rows(q.to(dev), scoring.QUERY_PREP[score])
+        master = scoring.prepare_rows(c.to(dev), scoring.CORPUS_PREP[score], want_bf16=False)
+        lists, kprime, m = [], None, None
+        for r in range(G):
+            s, e = sharded.shard_bounds(N, G, r)
+            index = qst_b200.CorpusIndex(c[s:e].to(dev), score, idx_offset=s)
+            plan = scoring.make_plan(Q, e - s, D, k, 0, score)
+            kprime = plan.kprime
+            m = sharded.candidates_per_shard(kprime, G)
+            ws = torch.empty(plan.ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), index.rows.bf16.data_ptr(),
+                                            ws.data_ptr(), _lib.stream_ptr(dev)))
+            out = torch.empty((Q, m + 1, 2), dtype=torch.int32, device=dev)
+            _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, s, out.data_ptr(), _lib.stream_ptr(dev)))
+            lists.append(out)
+            # list sanity: trailer count <= m, ids inside the shard
+            cnt = out[:, m, 1]
+            assert int(cnt.max()) <= m and int(cnt.min()) > 0
+            ids = out[:, :m, 1].long() & 0xffffffff
+            valid = torch.arange(m, device=dev)[None, :] < cnt[:, None]
+            assert bool(((ids >= s) & (ids < e))[valid].all())
+        recv = torch.stack(lists)                          # what the owner of all queries would receive
+        vals = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        margin = torch.empty(Q, dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.qst_finalize_lists_scratch_bytes(Q, G), dtype=torch.uint8, device=dev)
+        cos = score == "cos_sim"
+        _lib.check(lib.qst_finalize_lists(Q, G, m, k, kprime, scoring.SCORE_CODES[score], D, recv.data_ptr(),
+                                          pq.f32.data_ptr(), pq.inv_norm.data_ptr() if cos else None,
+                                          pq.err.data_ptr(), master.f32.data_ptr(),
+                                          master.inv_norm.data_ptr() if cos else None, master.stats.data_ptr(),
+                                          vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), scratch.data_ptr(),
+                                          _lib.stream_ptr(dev)))
+        if score == "dot_score":
+            scale = float(want_val.abs().max())
+            torch.testing.assert_close(vals.cpu() / scale, want_val / scale, rtol=0, atol=2e-6)
+            assert (idx.cpu() == want_idx).float().mean() > 0.999
+        else:
+            assert_same_ranking(idx, vals, want_idx, want_val, f"candidate exchange {score}")
+        assert bool((margin > 0).all()), score
