@@ -346,10 +346,12 @@ def run_ours(args):
 
     for _ in range(warmup):
         out = step_device()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, float(os.environ.get("QST_BENCH_CLOCK_PERIOD", "0.02")))
     sampler.start()
     ms_step, out = timed(step_device, steps)
     clocks = sampler.stop()
+    if corp is not None and corp._timing is not None:
+        sys.stderr.write(f"[rank {rank}] stage ms: " + corp.timing_report() + "\n")
     margin = out[2]
     uncertified = int((margin <= 0).sum())
 

@@ -83,6 +83,18 @@ for _ in range(10):
 b.record()
 t_host = (time.perf_counter() - t0) / 10 * 1e3
 torch.cuda.synchronize()
-if rank == 0:
-    print(f"corp.topk back-to-back: {a.elapsed_time(b) / 10:.3f} ms/step on the device, host enqueue {t_host:.3f} ms/step")
+print(f"[rank {rank}] corp.topk back-to-back: {a.elapsed_time(b) / 10:.3f} ms/step on the device, host enqueue {t_host:.3f} ms/step", flush=True)
+# same again, but exactly as bench.py brackets it
+def barrier():
+    dist.barrier()
+    torch.cuda.synchronize()
+for rep in range(2):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        out = corp.topk(queries, K)
+    e1.record()
+    barrier()
+    print(f"[rank {rank}] bench-style bracket rep {rep}: {e0.elapsed_time(e1) / 10:.3f} ms/step", flush=True)
 dist.destroy_process_group()

@@ -635,11 +635,13 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   if (sm_count <= 0) sm_count = 148;
   if (kprime <= 0) {
     // head-room so that the bf16 ordering error cannot push a true top-k document out of the
-    // candidate set (DESIGN.md "certificate"): k + max(3k/4, 32), in steps of 32
-    int extra = (3 * k) / 4 > 32 ? (3 * k) / 4 : 32;
-    kprime = (int)round_up(k + extra, 32);
+    // rescored set (DESIGN.md "certificate"): k + max(1.2 k, 40), in steps of 16.  Measured on
+    // config 3: k' = 192 leaves 1 query in 20 000 uncertified, k' = 224 none.
+    int extra = (6 * k) / 5 > 40 ? (6 * k) / 5 : 40;
+    kprime = k + extra;
   }
-  kprime = (int)round_up(kprime, 32);
+  kprime = (int)round_up(kprime, 16);
+  if (kprime > 2048) kprime = 2048;
   QST_CHECK_ARG(kprime >= k && kprime <= 2048, "plan_make: kprime %d out of range [k, 2048]", kprime);
   memset(plan, 0, sizeof(*plan));
   plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim_for(D, score == QST_SCORE_EUCLID ? QST_PREP_EUCLID_CORPUS : QST_PREP_RAW);
@@ -683,11 +685,14 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   // below the k'-th best score overall, so with S stripes a unit needs ~k'/S entries plus slack
   // for uneven placement; QST_KUNIT overrides (kunit = kprime is the most conservative setting).
   {
-    int ku = (int)round_up(2 * (int)ceil_div(kprime, plan->stripes) + 8, 16);
-    if (ku < 16) ku = 16;
+    // Poisson tail: a stripe holds ~k'/S of the k' best documents; 3x that plus 16 keeps the chance
+    // that a unit's threshold climbs above the k'-th best score negligible (kunit = 16 at 28 stripes
+    // left 56 of 20 000 queries uncertified, kunit = 32 none)
+    int ku = (int)round_up(3 * (int)ceil_div(kprime, plan->stripes) + 16, 8);
+    if (ku < 24) ku = 24;
     if (ku > kprime) ku = kprime;
     const char* e = getenv("QST_KUNIT");
-    if (e && atoi(e) >= 16) { ku = (int)round_up(atoi(e), 16); if (ku > kprime) ku = kprime; }
+    if (e && atoi(e) >= 8) { ku = (int)round_up(atoi(e), 8); if (ku > kprime) ku = kprime; }
     plan->kunit = ku;
     // slack between compactions: at least 128 entries
     plan->cap = 2 * ku > ku + 128 ? 2 * ku : ku + 128;

@@ -26,6 +26,7 @@ space instead of time.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -102,6 +103,7 @@ class ShardedCorpus:
         self.index = scoring.CorpusIndex(shard_embeddings, score, idx_offset=self.start)
         self.query_tile = query_tile
         self._side = torch.cuda.Stream(device=self.index.device) if self.world > 1 else None
+        self._timing = [] if os.environ.get("QST_SHARD_TIMING") else None   # debug: per-stage CUDA events
         self.master = None
         if full_master is not None:
             if full_master.shape[0] != n_total:
@@ -122,6 +124,23 @@ class ShardedCorpus:
             return self._topk_candidate_exchange(queries, k, kprime, exact)
         return self._topk_list_exchange(queries, k, kprime, exact)
 
+    def _mark(self, marks, name):
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    def timing_report(self) -> str:
+        """Mean per-stage device time of the calls made so far (QST_SHARD_TIMING=1)."""
+        if not self._timing:
+            return ""
+        torch.cuda.synchronize()
+        acc = {}
+        for marks in self._timing[len(self._timing) // 2:]:
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                acc.setdefault(n1, []).append(e0.elapsed_time(e1))
+        return "  ".join(f"{n} {sum(v) / len(v):.3f}" for n, v in acc.items())
+
     # ---- master="replicated": lists of bf16 candidates go to the owner of each query -----------
     def _topk_candidate_exchange(self, queries, k, kprime, exact):
         lib = _lib.load()
@@ -133,19 +152,25 @@ class ShardedCorpus:
         score = self.score
         cos = score == "cos_sim"
         code = scoring.SCORE_CODES[score]
+        marks = [] if self._timing is not None else None
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
+            self._mark(marks, "start")
             if q_pad != Q:     # pad with copies of the last query so that every rank owns q_own rows
                 queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
             pq = scoring.prepare_rows(queries, scoring.QUERY_PREP[score])
+            self._mark(marks, "prep")
             plan = scoring.make_plan(q_pad, self.index.n, self.index.d, k, kprime, score)
             m = candidates_per_shard(plan.kprime, G)
             ws = scoring._workspace(plan.ws_bytes, dev, "select")
             _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
                                             ws.data_ptr(), st))
+            self._mark(marks, "K2")
             lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
             _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
+            self._mark(marks, "select")
             recv = exchange_candidate_lists(lists, self.group)              # [G, q_own, m+1, 2]
+            self._mark(marks, "all_to_all")
             own = slice(self.rank * q_own, (self.rank + 1) * q_own)
             vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
@@ -160,15 +185,20 @@ class ShardedCorpus:
                                               mst.f32.data_ptr(), mst.inv_norm.data_ptr() if cos else None,
                                               mst.stats.data_ptr(), vals.data_ptr(), idx.data_ptr(),
                                               margin.data_ptr(), scratch.data_ptr(), st))
+            self._mark(marks, "finalize_lists")
             if exact:
                 rs = scoring._workspace(lib.qst_exact_rescan_workspace_bytes(q_own, k), dev, "rescan")
                 _lib.check(lib.qst_exact_rescan(q_own, self.n_total, self.index.d, k, code, q_f32.data_ptr(),
                                                 _lib.ptr(q_inv), mst.f32.data_ptr(),
                                                 mst.inv_norm.data_ptr() if cos else None, 0, vals.data_ptr(),
                                                 idx.data_ptr(), margin.data_ptr(), rs.data_ptr(), st))
+            self._mark(marks, "rescan")
             gv, gi = all_gather_topk(vals, idx, self.group)                 # [G, q_own, k]
             gm = torch.empty(q_pad, dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(gm, margin, group=self.group)
+            self._mark(marks, "all_gather")
+            if marks is not None:
+                self._timing.append(marks)
         return gv.view(q_pad, k)[:Q], gi.view(q_pad, k)[:Q], gm[:Q]
 
     # ---- master="sharded": exact per-shard top-k lists, all-gather, merge ---------------------------
