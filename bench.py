@@ -312,16 +312,19 @@ def run_ours(args):
         r = scoring.topk(queries, index, TOPK)
         return r.values, r.indices, r.margin
 
+    host_out = {}
+
     def step_host():
         if corp is not None:
             qd = queries_host.to(dev, non_blocking=True)
             v, i, _ = corp.topk(qd, TOPK)
-            vh = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-            ih = torch.empty(i.shape, dtype=i.dtype, pin_memory=True)
-            vh.copy_(v, non_blocking=True)
-            ih.copy_(i, non_blocking=True)
+            if not host_out:   # pinned result buffers are allocated once (cudaHostAlloc costs ms)
+                host_out["v"] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                host_out["i"] = torch.empty(i.shape, dtype=i.dtype, pin_memory=True)
+            host_out["v"].copy_(v, non_blocking=True)
+            host_out["i"].copy_(i, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return vh, ih
+            return host_out["v"], host_out["i"]
         return scoring.topk_host(queries_host, index, TOPK)
 
     def barrier():
