@@ -312,16 +312,56 @@ __global__ void __launch_bounds__(kQuadThreads) quad_kernel(const QuadArgs g) {
   }
 }
 
+// Cross-CTA loss reduction for the persistent fused kernel, placed BEFORE a warp's last gradient
+// stores so that its fence / ticket latency overlaps them.  Warps 1..3 only arrive on a named
+// barrier and move on; warp 0 collects the CTA sum, publishes it and takes a ticket; the CTA that
+// draws the last ticket sums all partials in a fixed order (deterministic result).
+__device__ __forceinline__ void post_cta_loss(const QuadArgs& g, double warp_sum_d, double* s_part, int warp, int lane) {
+  constexpr int kWarps = kQuadThreads / 32;
+  if (lane == 0) s_part[warp] = warp_sum_d;
+  if (warp != 0) {
+    __threadfence_block();
+    asm volatile("bar.arrive 1, %0;" ::"n"(kQuadThreads) : "memory");
+    return;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kQuadThreads) : "memory");
+  unsigned int ticket = 0;
+  if (lane == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) tot += s_part[w];
+    g.ws->partial[blockIdx.x] = tot;
+    __threadfence();
+    ticket = atomicAdd(&g.ws->counter, 1u);
+  }
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket == gridDim.x - 1) {
+    __threadfence();
+    double acc2 = 0.0;
+    for (int i = lane; i < (int)gridDim.x; i += 32) acc2 += __ldcg(&g.ws->partial[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+    if (lane == 0) {
+      if (g.reduction == QST_RED_MEAN) acc2 /= (double)g.B;
+      g.loss_out[0] = (float)acc2;
+      g.ws->counter = 0u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Register-resident fused forward+backward for rows of at most 32*VEC*kRegChunks elements
 // (1024 fp32 / 2048 half): the four rows are loaded ONCE with every 128-bit load issued up front
 // (kRegChunks*4 independent loads per thread), distances, loss terms and all four gradients are
 // computed from registers.  HBM traffic = the algorithmic 8*B*D*sizeof(T), nothing re-read.
 // ------------------------------------------------------------------------------------------
-constexpr int kRegChunks = 8;
+constexpr int kRegChunksMax = 8;
 
-template <typename T, int PM>
+// NCH = 16-byte chunks per lane and input row (row length <= 32*VEC*NCH): sized to the row so that
+// short rows do not pay registers (occupancy) for the longest supported one
+template <typename T, int PM, int NCH>
 __global__ void __launch_bounds__(kQuadThreads) quad_fused_reg_kernel(const QuadArgs g) {
+  constexpr int kRegChunks = NCH;
   constexpr int VEC = 16 / sizeof(T);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -331,6 +371,9 @@ __global__ void __launch_bounds__(kQuadThreads) quad_fused_reg_kernel(const Quad
   const float eps = g.prm.eps, p = g.prm.p;
   const bool swap = g.prm.swap != 0;
   double block_sum = 0.0;
+  __shared__ double s_part[kWarps];
+  bool posted = false;
+  const int64_t row_stride = (int64_t)gridDim.x * kWarps;
 
   for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < g.B; row += (int64_t)gridDim.x * kWarps) {
     const T* a = reinterpret_cast<const T*>(g.a) + row * D;
@@ -373,6 +416,10 @@ __global__ void __launch_bounds__(kQuadThreads) quad_fused_reg_kernel(const Quad
     const RowTerms t = row_terms(d, g.prm);
     if (lane == 0 && g.reduction == QST_RED_NONE) g.loss_out[row] = t.loss;
     block_sum += (double)t.loss;
+    if (g.reduction != QST_RED_NONE && row + row_stride >= g.B) {   // this warp's last row
+      post_cta_loss(g, block_sum, s_part, warp, lane);
+      posted = true;
+    }
 
     const float up = g.upstream * inv_b;
     float cnt[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
@@ -437,44 +484,27 @@ __global__ void __launch_bounds__(kQuadThreads) quad_fused_reg_kernel(const Quad
     }
   }
 
-  if (g.reduction != QST_RED_NONE) {
-    __shared__ double s_part[kWarps];
-    __shared__ bool s_last;
-    if (lane == 0) s_part[warp] = block_sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) tot += s_part[w];
-      g.ws->partial[blockIdx.x] = tot;
-      __threadfence();
-      const unsigned int ticket = atomicAdd(&g.ws->counter, 1u);
-      s_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last && warp == 0) {
-      __threadfence();
-      double acc2 = 0.0;
-      for (int i = lane; i < (int)gridDim.x; i += 32) acc2 += __ldcg(&g.ws->partial[i]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-      if (lane == 0) {
-        if (g.reduction == QST_RED_MEAN) acc2 /= (double)g.B;
-        g.loss_out[0] = (float)acc2;
-        g.ws->counter = 0u;
-      }
-    }
+  if (g.reduction != QST_RED_NONE && !posted) post_cta_loss(g, block_sum, s_part, warp, lane);   // warp had no row
+}
+
+template <typename T, int NCH>
+static void launch_fused_reg_n(const QuadArgs& a, int pm, int grid, cudaStream_t st) {
+  switch (pm) {
+    case PM_2: quad_fused_reg_kernel<T, PM_2, NCH><<<grid, kQuadThreads, 0, st>>>(a); break;
+    case PM_1: quad_fused_reg_kernel<T, PM_1, NCH><<<grid, kQuadThreads, 0, st>>>(a); break;
+    case PM_INF: quad_fused_reg_kernel<T, PM_INF, NCH><<<grid, kQuadThreads, 0, st>>>(a); break;
+    default: quad_fused_reg_kernel<T, PM_GEN, NCH><<<grid, kQuadThreads, 0, st>>>(a); break;
   }
 }
 
 template <typename T>
 static void launch_fused_reg(const QuadArgs& a, int pm, int grid, cudaStream_t st) {
-  switch (pm) {
-    case PM_2: quad_fused_reg_kernel<T, PM_2><<<grid, kQuadThreads, 0, st>>>(a); break;
-    case PM_1: quad_fused_reg_kernel<T, PM_1><<<grid, kQuadThreads, 0, st>>>(a); break;
-    case PM_INF: quad_fused_reg_kernel<T, PM_INF><<<grid, kQuadThreads, 0, st>>>(a); break;
-    default: quad_fused_reg_kernel<T, PM_GEN><<<grid, kQuadThreads, 0, st>>>(a); break;
-  }
+  const int64_t per_chunk = 32 * (16 / sizeof(T));
+  const int nch = (int)ceil_div(a.D, per_chunk);
+  if (nch <= 2) launch_fused_reg_n<T, 2>(a, pm, grid, st);
+  else if (nch <= 4) launch_fused_reg_n<T, 4>(a, pm, grid, st);
+  else if (nch <= 6) launch_fused_reg_n<T, 6>(a, pm, grid, st);
+  else launch_fused_reg_n<T, 8>(a, pm, grid, st);
 }
 
 template <typename T, int VEC, int KIND>
@@ -524,8 +554,18 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
     else if (kind == K_BWD) launch_vec<T, K_BWD>(a, pm, vec_ok, grid, st);   \
     else launch_vec<T, K_FUSED>(a, pm, vec_ok, grid, st);                    \
   } while (0)
-  const bool reg_path = kind == K_FUSED && vec_ok && a.D <= (int64_t)32 * vec * kRegChunks;
+  const bool reg_path = kind == K_FUSED && vec_ok && a.D <= (int64_t)32 * vec * kRegChunksMax;
   if (reg_path) {
+    // exactly one resident wave of CTAs (3 per SM at <= 168 registers), each looping over rows:
+    // fewer partials and tickets in the cross-CTA reduction, no ragged last wave
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    if (grid > sms * 3) grid = sms * 3;
     if (dtype == QST_F32) launch_fused_reg<float>(a, pm, grid, st);
     else if (dtype == QST_F16) launch_fused_reg<__half>(a, pm, grid, st);
     else launch_fused_reg<__nv_bfloat16>(a, pm, grid, st);
