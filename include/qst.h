@@ -168,6 +168,27 @@ int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kprime, int s
 int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16,
                      void* workspace, qst_stream_t stream);
 
+/* Corpus-sharded variant of K2: every rank scores the SAME queries against its
+ * own shard; the per-row thresholds are shared between ranks THROUGH PEER MEMORY while the kernels
+ * run -- a rank that establishes a better threshold for a query pushes it with a remote atomicMax
+ * (NVLink/NVSwitch) into the hint array of every peer, so all shards filter against the best
+ * threshold found anywhere.  hint_local / peer_hints[i] are [plan->m_tiles * plan->rows_per_unit]
+ * uint32 arrays in buffers from qst_peer_buffer_create / _open; the caller zeroes hint_local before
+ * the launch (and keeps two generations so a fast rank never pushes into a buffer being cleared).
+ * Purely opportunistic: no rank ever waits on another inside the kernel. */
+#define QST_MAX_PEERS 15
+#define QST_IPC_HANDLE_BYTES 64
+int qst_score_select_peers(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
+                           void* hint_local, void* const* peer_hints, int n_peers, qst_stream_t stream);
+/* Device buffers other processes on the node can map (CUDA IPC).  create: cudaMalloc + zero fill +
+ * export handle (64 bytes, to be exchanged by the caller, e.g. with an all-gather); open: map a
+ * peer's buffer into this process; close / destroy undo them. */
+int qst_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int qst_peer_buffer_open(const unsigned char* handle64, void** dev_ptr);
+int qst_peer_buffer_clear(void* dev_ptr, size_t offset, size_t bytes, qst_stream_t stream);
+int qst_peer_buffer_close(void* peer_ptr);
+int qst_peer_buffer_destroy(void* dev_ptr);
+
 /* Debug/validation aid: raw tensor-core scores of one call written densely, out[Q, N] fp32.
  * Same kernel, same tiles, epilogue stores instead of selecting.  Small shapes only. */
 int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad,

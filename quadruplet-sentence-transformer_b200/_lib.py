@@ -67,6 +67,12 @@ SIGNATURES = {
     "qst_topk_plan_make": (_INT, [_I64, _I64, _I64, _INT, _INT, _INT, _INT, C.POINTER(TopkPlan)]),
     "qst_score_select": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P]),
     "qst_score_dense": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
+    "qst_score_select_peers": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, C.POINTER(_P), _INT, _P]),
+    "qst_peer_buffer_create": (_INT, [C.c_size_t, C.POINTER(_P), C.c_char_p]),
+    "qst_peer_buffer_open": (_INT, [C.c_char_p, C.POINTER(_P)]),
+    "qst_peer_buffer_clear": (_INT, [_P, C.c_size_t, C.c_size_t, _P]),
+    "qst_peer_buffer_close": (_INT, [_P]),
+    "qst_peer_buffer_destroy": (_INT, [_P]),
     "qst_finalize_topk": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "qst_select_candidates": (_INT, [C.POINTER(TopkPlan), _P, _INT, _I64, _P, _P]),
     "qst_finalize_lists_scratch_bytes": (C.c_size_t, [_I64, _INT]),

@@ -24,3 +24,53 @@ extern "C" int qst_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_minor) { QST_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
   return QST_OK;
 }
+
+// ---- peer-visible device buffers (CUDA IPC) for the cross-rank threshold hints ------------------
+extern "C" int qst_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  QST_CHECK_ARG(dev_ptr && handle64 && bytes > 0, "peer_buffer_create: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == QST_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  QST_CUDA(cudaMalloc(&p, bytes));
+  QST_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    qst::set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return QST_ERR_CUDA;
+  }
+  memcpy(handle64, &h, sizeof(h));
+  *dev_ptr = p;
+  return QST_OK;
+}
+
+extern "C" int qst_peer_buffer_open(const unsigned char* handle64, void** dev_ptr) {
+  QST_CHECK_ARG(dev_ptr && handle64, "peer_buffer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    qst::set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    return QST_ERR_CUDA;
+  }
+  *dev_ptr = p;
+  return QST_OK;
+}
+
+extern "C" int qst_peer_buffer_clear(void* dev_ptr, size_t offset, size_t bytes, qst_stream_t stream) {
+  QST_CHECK_ARG(dev_ptr != nullptr, "peer_buffer_clear: null pointer");
+  QST_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(dev_ptr) + offset, 0, bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return QST_OK;
+}
+
+extern "C" int qst_peer_buffer_close(void* peer_ptr) {
+  if (peer_ptr) QST_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return QST_OK;
+}
+
+extern "C" int qst_peer_buffer_destroy(void* dev_ptr) {
+  if (dev_ptr) QST_CUDA(cudaFree(dev_ptr));
+  return QST_OK;
+}

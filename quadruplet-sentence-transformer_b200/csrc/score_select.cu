@@ -64,6 +64,11 @@ struct ScoreParams {
   uint32_t* unit_thr;  // [units*UNIT_ROWS] final threshold key of the unit row (upper bound of its discards)
   uint2* unit_cand;    // [units*UNIT_ROWS*cap]  (key, corpus row)
   float* dense_out;    // dense mode only: [Q, N]
+  // corpus-sharded runs: hint arrays of the OTHER ranks (peer-mapped device memory over
+  // NVLink/NVSwitch).  A new row threshold is pushed to every peer with a remote atomicMax, so all
+  // shards filter against the best threshold any shard has established for the query.
+  uint32_t* peer_hint[QST_MAX_PEERS];
+  int n_peers;
   int debug;           // QST_SCORE_DEBUG ablation bits (0 in production), see launch_score()
 };
 
@@ -241,6 +246,7 @@ __device__ __forceinline__ void compact_rows(unsigned need, int max_keep, const 
       cnt = n_new;
       thr = fmaxf(thr, key_to_float(T));
       atomicMax(&P.thr_hint[grow], T);
+      for (int pr = 0; pr < P.n_peers; ++pr) atomicMax(&P.peer_hint[pr][grow], T);   // remote RED, fire and forget
     }
   }
 }
@@ -708,8 +714,26 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   return QST_OK;
 }
 
+static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
+                             uint32_t* hint_local, uint32_t* const* peer_hints, int n_peers, qst_stream_t stream);
+
 extern "C" int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
                                 qst_stream_t stream) {
+  return score_select_impl(plan, q_bf16, c_bf16, workspace, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int qst_score_select_peers(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16,
+                                      void* workspace, void* hint_local, void* const* peer_hints, int n_peers,
+                                      qst_stream_t stream) {
+  QST_CHECK_ARG(hint_local != nullptr, "score_select_peers: null hint_local");
+  QST_CHECK_ARG(n_peers >= 0 && n_peers <= QST_MAX_PEERS, "score_select_peers: n_peers=%d out of range", n_peers);
+  QST_CHECK_ARG(n_peers == 0 || peer_hints != nullptr, "score_select_peers: null peer_hints");
+  return score_select_impl(plan, q_bf16, c_bf16, workspace, reinterpret_cast<uint32_t*>(hint_local),
+                           reinterpret_cast<uint32_t* const*>(peer_hints), n_peers, stream);
+}
+
+static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
+                             uint32_t* hint_local, uint32_t* const* peer_hints, int n_peers, qst_stream_t stream) {
   QST_CHECK_ARG(plan && q_bf16 && c_bf16 && workspace, "score_select: null argument");
   QST_CHECK_ARG((reinterpret_cast<uintptr_t>(q_bf16) & 15u) == 0 && (reinterpret_cast<uintptr_t>(c_bf16) & 15u) == 0,
                 "score_select: operands must be 16-byte aligned");
@@ -720,12 +744,17 @@ extern "C" int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, c
   P.m_tiles = plan->m_tiles; P.n_tiles = plan->n_tiles; P.stripes = plan->stripes;
   P.tiles_per_stripe = plan->tiles_per_stripe; P.units = plan->units;
   P.kunit = plan->kunit; P.cap = plan->cap;
-  P.thr_hint = reinterpret_cast<uint32_t*>(ws + plan->off_thr);
+  // hint array: inside the workspace (zeroed here) or, for sharded runs, the caller's peer-visible
+  // buffer, which the CALLER zeroes (it is written by other ranks, see qst_peer_buffer_*)
+  P.thr_hint = hint_local ? hint_local : reinterpret_cast<uint32_t*>(ws + plan->off_thr);
+  for (int i = 0; i < n_peers; ++i) P.peer_hint[i] = peer_hints[i];
+  P.n_peers = n_peers;
   P.unit_cnt = reinterpret_cast<int*>(ws + plan->off_cnt);
   P.unit_thr = reinterpret_cast<uint32_t*>(ws + plan->off_uthr);
   P.unit_cand = reinterpret_cast<uint2*>(ws + plan->off_cand);
   QST_CHECK_ARG(plan->ctas == 1 || plan->ctas == 2, "score_select: plan->ctas must be 1 or 2");
-  QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * plan->rows_per_unit * sizeof(uint32_t), st));
+  if (!hint_local)
+    QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * plan->rows_per_unit * sizeof(uint32_t), st));
   return launch_score(plan->ctas, false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
 }
 

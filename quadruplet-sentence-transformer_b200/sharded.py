@@ -86,6 +86,70 @@ def exchange_candidate_lists(lists: torch.Tensor, group=None) -> torch.Tensor:
     return out.view((world, lists.shape[0] // world) + tuple(lists.shape[1:]))
 
 
+class PeerHints:
+    """Threshold-hint arrays every rank of the node can write (CUDA IPC), two generations.
+
+    Rank r's K2 pushes a query's new threshold into the hint array of every peer with a remote
+    atomicMax over NVLink, so all shards filter against the best threshold found on ANY shard
+    (``qst_score_select_peers``).  Generation g is used by step g mod 2 and cleared (stream-ordered)
+    right after the previous step's K2, so a fast rank never pushes into memory that a slow rank is
+    about to clear, and hints of one step never leak into the next (different queries).
+    """
+
+    def __init__(self, rows: int, group, device: torch.device):
+        lib = _lib.load()
+        self.rows, self.group, self.device = rows, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.gen_bytes = ((rows * 4 + 255) // 256) * 256
+        self.step = 0
+        self.local = C.c_void_p()
+        self.peers = []
+        handle = C.create_string_buffer(64)
+        ok = 1
+        with torch.cuda.device(device):
+            if lib.qst_peer_buffer_create(2 * self.gen_bytes, C.byref(self.local), handle) != 0:
+                ok, self.local = 0, C.c_void_p()
+            mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().view(self.world, 64)
+            if ok:
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    p = C.c_void_p()
+                    if lib.qst_peer_buffer_open(bytes(every[r].tolist()), C.byref(p)) != 0:
+                        ok = 0
+                        break
+                    self.peers.append(p)
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
+        self.ok = bool(int(flag))
+        if not self.ok:
+            self.close()
+
+    def launch_args(self):
+        """(local pointer, ctypes array of peer pointers, n_peers) of the current generation."""
+        off = (self.step % 2) * self.gen_bytes
+        arr = (C.c_void_p * max(1, len(self.peers)))(*[C.c_void_p(p.value + off) for p in self.peers])
+        return C.c_void_p(self.local.value + off), arr, len(self.peers)
+
+    def advance(self, stream_ptr):
+        """Call right after K2 was enqueued: clear the other generation for the next step."""
+        nxt = ((self.step + 1) % 2) * self.gen_bytes
+        _lib.check(_lib.load().qst_peer_buffer_clear(self.local, nxt, self.gen_bytes, stream_ptr))
+        self.step += 1
+
+    def close(self):
+        lib = _lib.load()
+        for p in self.peers:
+            lib.qst_peer_buffer_close(p)
+        self.peers = []
+        if self.local:
+            lib.qst_peer_buffer_destroy(self.local)
+            self.local = C.c_void_p()
+
+
 class ShardedCorpus:
     """This rank's shard of an N-row corpus + the collective top-k over all shards."""
 
@@ -103,6 +167,8 @@ class ShardedCorpus:
         self.index = scoring.CorpusIndex(shard_embeddings, score, idx_offset=self.start)
         self.query_tile = query_tile
         self._side = torch.cuda.Stream(device=self.index.device) if self.world > 1 else None
+        self._peer_hints: Optional[PeerHints] = None
+        self._peer_hints_off = bool(os.environ.get("QST_NO_PEER_HINTS"))
         self._timing = [] if os.environ.get("QST_SHARD_TIMING") else None   # debug: per-stage CUDA events
         self.master = None
         if full_master is not None:
@@ -123,6 +189,21 @@ class ShardedCorpus:
         if self.master is not None:
             return self._topk_candidate_exchange(queries, k, kprime, exact)
         return self._topk_list_exchange(queries, k, kprime, exact)
+
+    def _hints_for(self, rows: int, dev) -> Optional[PeerHints]:
+        """Peer-visible hint arrays for `rows` query rows (collective on first use / growth)."""
+        if self._peer_hints_off:
+            return None
+        if self._peer_hints is None or self._peer_hints.rows < rows:
+            if self._peer_hints is not None:
+                torch.cuda.synchronize(dev)
+                dist.barrier(self.group)          # nobody may still be pushing into the old buffers
+                self._peer_hints.close()
+            self._peer_hints = PeerHints(rows, self.group, dev)
+            if not self._peer_hints.ok:
+                self._peer_hints_off = True       # IPC not available here: per-shard thresholds only
+                return None
+        return self._peer_hints
 
     def _mark(self, marks, name):
         if marks is not None:
@@ -160,11 +241,22 @@ class ShardedCorpus:
                 queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
             pq = scoring.prepare_rows(queries, scoring.QUERY_PREP[score])
             self._mark(marks, "prep")
-            plan = scoring.make_plan(q_pad, self.index.n, self.index.d, k, kprime, score)
-            m = candidates_per_shard(plan.kprime, G)
+            # k' of the whole corpus decides how many candidates every shard lists (m); the shard's
+            # own K2 then only has to retain its m best
+            kprime_all = scoring.make_plan(q_pad, self.n_total, self.index.d, k, kprime, score).kprime
+            m = candidates_per_shard(kprime_all, G)
+            plan = scoring.make_plan(q_pad, self.index.n, self.index.d, min(k, m), m, score)
             ws = scoring._workspace(plan.ws_bytes, dev, "select")
-            _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
-                                            ws.data_ptr(), st))
+            hints = self._hints_for(plan.m_tiles * plan.rows_per_unit, dev)
+            if hints is not None:
+                local, peers, n_peers = hints.launch_args()
+                _lib.check(lib.qst_score_select_peers(C.byref(plan), pq.bf16.data_ptr(),
+                                                      self.index.rows.bf16.data_ptr(), ws.data_ptr(), local, peers,
+                                                      n_peers, st))
+                hints.advance(st)
+            else:
+                _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+                                                ws.data_ptr(), st))
             self._mark(marks, "K2")
             lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
             _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
@@ -180,7 +272,7 @@ class ShardedCorpus:
             q_f32 = pq.f32[own]
             q_inv = pq.inv_norm[own] if cos else None
             q_err = pq.err[own]
-            _lib.check(lib.qst_finalize_lists(q_own, G, m, k, plan.kprime, code, self.index.d, recv.data_ptr(),
+            _lib.check(lib.qst_finalize_lists(q_own, G, m, k, kprime_all, code, self.index.d, recv.data_ptr(),
                                               q_f32.data_ptr(), _lib.ptr(q_inv), q_err.data_ptr(),
                                               mst.f32.data_ptr(), mst.inv_norm.data_ptr() if cos else None,
                                               mst.stats.data_ptr(), vals.data_ptr(), idx.data_ptr(),
