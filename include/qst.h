@@ -164,6 +164,11 @@ typedef struct qst_topk_plan {
 int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kprime, int score, int sm_count,
                        qst_topk_plan* plan);
 
+/* Overrides the number of entries a work unit keeps per row (and the derived buffer capacity and
+ * workspace layout).  Used by the corpus-sharded path, where the relevant count is k' of the WHOLE
+ * corpus spread over the units of ALL shards. */
+int qst_topk_plan_set_kunit(qst_topk_plan* plan, int kunit);
+
 /* K2.  q_bf16 [Q, D_pad], c_bf16 [N, D_pad] from qst_prep_rows.  Fills plan->ws. */
 int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16,
                      void* workspace, qst_stream_t stream);

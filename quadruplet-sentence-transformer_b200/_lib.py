@@ -65,6 +65,7 @@ SIGNATURES = {
     "qst_padded_dim_for": (_I64, [_I64, _INT]),
     "qst_prep_rows": (_INT, [_P, _INT, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "qst_topk_plan_make": (_INT, [_I64, _I64, _I64, _INT, _INT, _INT, _INT, C.POINTER(TopkPlan)]),
+    "qst_topk_plan_set_kunit": (_INT, [C.POINTER(TopkPlan), _INT]),
     "qst_score_select": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P]),
     "qst_score_dense": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
     "qst_score_select_peers": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, C.POINTER(_P), _INT, _P]),

@@ -629,6 +629,17 @@ static int device_sm_count() {
 
 using namespace qst;
 
+// workspace layout of a plan (depends on units, rows_per_unit, cap)
+static void plan_layout(qst_topk_plan* plan) {
+  size_t off = 0;
+  const size_t ur = (size_t)plan->rows_per_unit;
+  plan->off_thr = off;  off += round_up((size_t)plan->m_tiles * ur * sizeof(uint32_t), 256);
+  plan->off_cnt = off;  off += round_up((size_t)plan->units * ur * sizeof(int), 256);
+  plan->off_uthr = off; off += round_up((size_t)plan->units * ur * sizeof(uint32_t), 256);
+  plan->off_cand = off; off += (size_t)plan->units * ur * (size_t)plan->cap * sizeof(uint2);
+  plan->ws_bytes = off;
+}
+
 extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kprime, int score, int sm_count,
                                   qst_topk_plan* plan) {
   QST_CHECK_ARG(plan != nullptr, "plan_make: null plan");
@@ -704,15 +715,19 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
     plan->cap = 2 * ku > ku + 128 ? 2 * ku : ku + 128;
   }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
-  size_t off = 0;
-  const size_t ur = (size_t)plan->rows_per_unit;
-  plan->off_thr = off;  off += round_up((size_t)plan->m_tiles * ur * sizeof(uint32_t), 256);
-  plan->off_cnt = off;  off += round_up((size_t)plan->units * ur * sizeof(int), 256);
-  plan->off_uthr = off; off += round_up((size_t)plan->units * ur * sizeof(uint32_t), 256);
-  plan->off_cand = off; off += (size_t)plan->units * ur * (size_t)plan->cap * sizeof(uint2);
-  plan->ws_bytes = off;
+  plan_layout(plan);
   return QST_OK;
 }
+
+extern "C" int qst_topk_plan_set_kunit(qst_topk_plan* plan, int kunit) {
+  QST_CHECK_ARG(plan != nullptr, "plan_set_kunit: null plan");
+  QST_CHECK_ARG(kunit >= 8 && kunit <= 2048, "plan_set_kunit: kunit=%d out of range", kunit);
+  plan->kunit = (int)round_up(kunit, 8);
+  plan->cap = 2 * plan->kunit > plan->kunit + 128 ? 2 * plan->kunit : plan->kunit + 128;
+  plan_layout(plan);
+  return QST_OK;
+}
+
 
 static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
                              uint32_t* hint_local, uint32_t* const* peer_hints, int n_peers, qst_stream_t stream);

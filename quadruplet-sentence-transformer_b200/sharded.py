@@ -211,16 +211,23 @@ class ShardedCorpus:
             e.record()
             marks.append((name, e))
 
-    def timing_report(self) -> str:
-        """Mean per-stage device time of the calls made so far (QST_SHARD_TIMING=1)."""
+    def enable_stage_timing(self):
+        """Record CUDA events between the stages of every following call (cheap; for bench/profiling)."""
+        self._timing = []
+
+    def stage_ms(self) -> dict:
+        """Mean per-stage device time over the most recent half of the timed calls."""
         if not self._timing:
-            return ""
+            return {}
         torch.cuda.synchronize()
         acc = {}
         for marks in self._timing[len(self._timing) // 2:]:
             for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
                 acc.setdefault(n1, []).append(e0.elapsed_time(e1))
-        return "  ".join(f"{n} {sum(v) / len(v):.3f}" for n, v in acc.items())
+        return {n: sum(v) / len(v) for n, v in acc.items()}
+
+    def timing_report(self) -> str:
+        return "  ".join(f"{n} {v:.3f}" for n, v in self.stage_ms().items())
 
     # ---- master="replicated": lists of bf16 candidates go to the owner of each query -----------
     def _topk_candidate_exchange(self, queries, k, kprime, exact):
@@ -246,8 +253,14 @@ class ShardedCorpus:
             kprime_all = scoring.make_plan(q_pad, self.n_total, self.index.d, k, kprime, score).kprime
             m = candidates_per_shard(kprime_all, G)
             plan = scoring.make_plan(q_pad, self.index.n, self.index.d, min(k, m), m, score)
-            ws = scoring._workspace(plan.ws_bytes, dev, "select")
             hints = self._hints_for(plan.m_tiles * plan.rows_per_unit, dev)
+            if hints is not None:
+                # thresholds are shared by the units of ALL shards: size the per-unit retention for
+                # k' of the whole corpus spread over stripes x shards units (same Poisson-tail rule as
+                # qst_topk_plan_make)
+                ku = max(24, -(-(3 * -(-kprime_all // (plan.stripes * G)) + 16) // 8) * 8)
+                _lib.check(lib.qst_topk_plan_set_kunit(C.byref(plan), min(ku, plan.kunit)))
+            ws = scoring._workspace(plan.ws_bytes, dev, "select")
             if hints is not None:
                 local, peers, n_peers = hints.launch_args()
                 _lib.check(lib.qst_score_select_peers(C.byref(plan), pq.bf16.data_ptr(),
