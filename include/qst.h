@@ -101,6 +101,16 @@ int qst_quadruplet_fwd_bwd(const void* x_anchor, const void* x_pos, const void* 
                            void* g_anchor, void* g_pos, void* g_part, void* g_neg,
                            void* workspace, qst_stream_t stream);
 
+/* Paired distances of the QuadrupletEvaluator (models/evaluators.py:130-389: three ST 2.2.2
+ * TripletEvaluators pos/part, pos/neg, part/neg with sklearn paired cosine / manhattan / euclidean
+ * distances).  One pass over the four [B, D] matrices.
+ *   out_dist   [B, 9] fp32 or NULL: (cosine, manhattan, euclidean) x d(anchor, {pos, part, neg})
+ *   out_counts [9] uint64: (cosine, manhattan, euclidean) x #{pos<part, pos<neg, part<neg}
+ *              (zeroed by the call) */
+int qst_quadruplet_eval(const void* x_anchor, const void* x_pos, const void* x_part, const void* x_neg,
+                        int dtype, int64_t B, int64_t D, float* out_dist, unsigned long long* out_counts,
+                        qst_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1  row preparation.  Replaces the F.normalize(p=2, dim=1, eps=1e-12) half of
  * sentence_transformers.util.cos_sim (called at ir_evauation_script.py:70,

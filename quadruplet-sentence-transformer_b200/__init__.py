@@ -14,6 +14,7 @@ Public surface (same names and call signatures as the reference side uses):
 * ``InformationRetrievalEvaluator``, ``cos_sim``, ``dot_score``
   (sentence-transformers 2.2.2, as constructed at ``ir_evauation_script.py:107-123``) and the
   reference's own ``euclidean_score`` (``models/evaluators.py:392-405``)
+* ``QuadrupletEvaluator`` (``models/evaluators.py:130-389``) with its paired distances on the device
 * ``CorpusIndex``, ``topk``: the scoring engine underneath
 * ``ShardedCorpus``: corpus-sharded retrieval over NCCL
 
@@ -25,12 +26,14 @@ from .quad_loss import (GammaQuadrupletLoss, QuadrupletLoss, gamma_quadruplet_lo
                         gamma_quadruplet_loss_and_grads)
 from .scoring import (CorpusIndex, TopkResult, cos_sim, dot_score, euclidean_score, prepare_rows, topk,
                       topk_host)
-from .ir_evaluator import InformationRetrievalEvaluator
+from .ir_evaluator import InformationRetrievalEvaluator, load_ir_evaluation_set
+from .quad_evaluator import QuadrupletEvaluator, SimilarityFunction, paired_distance_counts
 from . import metrics, synth
 from .sharded import ShardedCorpus
 
 __all__ = [
     "GammaQuadrupletLoss", "QuadrupletLoss", "gamma_quadruplet_loss", "gamma_quadruplet_loss_and_grads",
     "InformationRetrievalEvaluator", "cos_sim", "dot_score", "euclidean_score", "CorpusIndex", "TopkResult", "topk",
-    "topk_host", "prepare_rows", "ShardedCorpus", "metrics", "synth", "QstError", "QstLibraryError",
+    "topk_host", "prepare_rows", "QuadrupletEvaluator", "SimilarityFunction", "paired_distance_counts",
+    "load_ir_evaluation_set", "ShardedCorpus", "metrics", "synth", "QstError", "QstLibraryError",
 ]

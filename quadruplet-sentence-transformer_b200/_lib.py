@@ -61,6 +61,7 @@ SIGNATURES = {
                                    _P, _P, _P, _P, _P]),
     "qst_quadruplet_fwd_bwd": (_INT, [_P, _P, _P, _P, _INT, _I64, _I64, C.POINTER(QuadParams), _INT, C.c_float,
                                        _P, _P, _P, _P, _P, _P, _P]),
+    "qst_quadruplet_eval": (_INT, [_P, _P, _P, _P, _INT, _I64, _I64, _P, _P, _P]),
     "qst_padded_dim": (_I64, [_I64]),
     "qst_padded_dim_for": (_I64, [_I64, _INT]),
     "qst_prep_rows": (_INT, [_P, _INT, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),

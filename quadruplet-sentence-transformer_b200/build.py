@@ -17,7 +17,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libqst.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["common.cu", "quad_loss.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu"]
+SOURCES = ["common.cu", "quad_loss.cu", "quad_eval.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu"]
 HEADERS = ["qst_common.cuh", "sm100_ptx.cuh"]
 
 NVCC_FLAGS = [

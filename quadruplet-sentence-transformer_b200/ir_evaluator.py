@@ -16,6 +16,7 @@ What changes underneath: embeddings stay on the GPU, scoring + top-k never mater
 """
 from __future__ import annotations
 
+import json
 import logging
 import os
 from typing import Callable, Dict, List, Optional, Set
@@ -27,6 +28,21 @@ from . import _lib, metrics, scoring
 from .scoring import cos_sim, dot_score, euclidean_score
 
 logger = logging.getLogger(__name__)
+
+
+def load_ir_evaluation_set(path: str):
+    """IR evaluation set written by ``create_ir_evaluation_set``
+    (``/root/reference/models/evaluators.py:438-442, 521-527``): JSON with ``queries`` {qid: text},
+    ``corpus`` {cid: text}, ``relevant`` {qid: [cid, ...]} and ``random_seed``.  Returns
+    ``(queries, corpus, relevant_docs)`` with the relevant lists turned into sets, which is what the
+    evaluator expects.  (The reference's own reload at ``models/evaluators.py:556-557`` /
+    ``ir_evauation_script.py:95-96`` does ``set(evaluation_queries["relevant"])`` -- the set of ALL query
+    ids -- for every query; this loader applies the evident intent, ``set(relevant[q])``.)
+    """
+    with open(path, "r") as fp:
+        data = json.load(fp)
+    relevant = {q: set(docs) for q, docs in data["relevant"].items()}
+    return data["queries"], data["corpus"], relevant
 
 
 class InformationRetrievalEvaluator:

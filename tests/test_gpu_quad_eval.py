@@ -1,0 +1,79 @@
+"""QuadrupletEvaluator paired distances against the sklearn-based oracle."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _quads(B, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, D, generator=g)
+    p = a + 0.4 * torch.randn(B, D, generator=g)
+    pp = a + 0.8 * torch.randn(B, D, generator=g)
+    n = torch.randn(B, D, generator=g)
+    return a, p, pp, n
+
+
+@pytest.mark.parametrize("B,D", [(257, 384), (64, 768), (5, 7), (1, 1)])
+def test_paired_distances_and_counts(B, D):
+    import qst_b200
+    from oracle import quad_eval_oracle as qo
+    a, p, pp, n = _quads(B, D, 14 + B)
+    counts, dist = qst_b200.paired_distance_counts(*[x.to(_dev()) for x in (a, p, pp, n)], want_distances=True)
+    dist = dist.cpu().numpy()
+    want = []
+    for other in (p, pp, n):
+        want.append(qo.paired_distances(a.numpy(), other.numpy()))
+    for m in range(3):                       # cos, manhattan, euclid
+        for k in range(3):                   # pos, part, neg
+            np.testing.assert_allclose(dist[:, m * 3 + k], want[k][m], rtol=2e-5, atol=2e-6)
+    # counts: identical to comparing the oracle's distances, except rows where the two distances
+    # are within float rounding of each other
+    for m in range(3):
+        for j, (x, y) in enumerate(((0, 1), (0, 2), (1, 2))):
+            dx, dy = want[x][m], want[y][m]
+            sure = np.abs(dx - dy) > 1e-5 * np.maximum(np.abs(dx), np.abs(dy))
+            lo = int(((dx < dy) & sure).sum())
+            hi = lo + int((~sure).sum())
+            assert lo <= int(counts[m, j]) <= hi, (m, j, lo, int(counts[m, j]), hi)
+
+
+def test_evaluator_protocol_and_csv(tmp_path):
+    import qst_b200
+    from oracle import quad_eval_oracle as qo
+    B, D = 300, 96
+    a, p, pp, n = _quads(B, D, 3)
+    table = torch.cat([a, p, pp, n]).to(_dev())
+    model = qst_b200.synth.TableModel(table)
+    ids = [[str(k * B + i) for i in range(B)] for k in range(4)]
+    for main, key in ((None, None), (qst_b200.SimilarityFunction.COSINE, "cos"),
+                      (qst_b200.SimilarityFunction.MANHATTAN, "manhattan"),
+                      (qst_b200.SimilarityFunction.EUCLIDEAN, "euclid")):
+        ev = qst_b200.QuadrupletEvaluator(*ids, gamma=0.6, main_distance_function=main, name="t")
+        got = ev(model, output_path=str(tmp_path), epoch=2, steps=7)
+        want, parts = qo.quadruplet_accuracy(a.numpy(), p.numpy(), pp.numpy(), n.numpy(), gamma=0.6, main=key)
+        assert abs(got - want) <= 2.0 / B, (main, got, want)
+        for k, v in parts.items():
+            assert abs(ev.last_accuracies[k] - v) <= 1.0 / B
+    rows = list(csv.reader(open(os.path.join(tmp_path, "quadruplet_evaluation_t_results.csv"))))
+    assert rows[0] == ["epoch", "steps", "pos_part_accuracy", "pos_neg_accuracy", "part_neg_accuracy", "global_accuracy"]
+    assert len(rows) == 5 and rows[1][:2] == ["2", "7"]
+    trip = list(csv.reader(open(os.path.join(tmp_path, "triplet_evaluation_pos_neg_results.csv"))))
+    assert trip[0] == ["epoch", "steps", "accuracy_cosinus", "accuracy_manhattan", "accuracy_euclidean"]
+    # sampling from dataset-style items (dict with lists) and InputExample-like objects
+    class Ex:
+        def __init__(self, t):
+            self.texts = t
+    items = [{"reference": "0", "positive": ["300", "301"], "part_positive": "600", "negative": ["900"]},
+             (Ex(["1", "301", "601", "901"]), 0)]
+    ev2 = qst_b200.QuadrupletEvaluator.from_input_examples(items, gamma=0.5)
+    assert ev2.anchors == ["0", "1"] and ev2.negatives == ["900", "901"] and ev2.positives[0] in ("300", "301")
+    assert 0.0 <= ev2(model) <= 1.0

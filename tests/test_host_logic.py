@@ -125,3 +125,26 @@ def test_synthetic_data_is_deterministic_and_planted():
         assert {f"d{int(j)}" for j in top[i]} <= relevant[f"q{i}"]
     xs = qst_b200.synth.quadruplet_batch(8, 16)
     assert len(xs) == 4 and xs[0].shape == (8, 16) and not torch.equal(xs[0], xs[1])
+
+
+def test_ir_evaluation_set_loader_and_quadruplet_evaluator_construction(tmp_path):
+    """the JSON written by create_ir_evaluation_set
+    (models/evaluators.py:438-442, 521-527) and the evaluator's host-side bookkeeping."""
+    import json
+    import qst_b200
+    path = tmp_path / "ir_evaluation_dataset.json"
+    json.dump({"queries": {"0": "a query", "1": "another"}, "corpus": {"0": "doc a", "2": "doc c", "5": "doc f"},
+               "relevant": {"0": ["0", "2"], "1": ["5", "5"]}, "random_seed": 14}, open(path, "w"))
+    queries, corpus, relevant = qst_b200.load_ir_evaluation_set(str(path))
+    assert relevant == {"0": {"0", "2"}, "1": {"5"}} and list(corpus) == ["0", "2", "5"]
+    ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
+        "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score})
+    assert ev._relevant_positions == [sorted(ev._relevant_positions[0]), [2]] and sorted(ev._relevant_positions[0]) == [0, 1]
+    qe = qst_b200.QuadrupletEvaluator(["a"], ["b"], ["c"], ["d"], gamma=0.25, name="n")
+    assert qe.csv_file == "quadruplet_evaluation_n_results.csv"
+    assert qe._pick(0.1, 0.3, 0.2) == 0.3
+    qe.main_distance_function = qst_b200.SimilarityFunction.EUCLIDEAN
+    assert qe._pick(0.1, 0.3, 0.2) == 0.2
+    assert [m.value for m in qst_b200.SimilarityFunction] == [0, 1, 2, 3]
+    with pytest.raises(AssertionError):
+        qst_b200.QuadrupletEvaluator(["a"], ["b", "x"], ["c"], ["d"])
