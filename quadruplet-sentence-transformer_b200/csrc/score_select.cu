@@ -290,9 +290,25 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
                   fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
   const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
   const bool hit = mx > thr;
-  unsigned hm = __ballot_sync(0xffffffffu, hit);
-  if (hm == 0u) return;
-  if (hit) {
+  if (__ballot_sync(0xffffffffu, hit) == 0u) return;
+  // Some lane has a score above its threshold.  Which ones: a 32-bit mask per lane (predicated, no
+  // branches).  The common case by far is ONE such score in the lane's 32 columns -- it is then the
+  // row maximum, and the lane appends it on its own, with no cross-lane traffic at all.  Lanes with
+  // two or more go through the staged, warp-cooperative path below.
+  unsigned above = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) above |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+  const int n_above = __popc(above);
+  if (n_above == 1) {
+    my_buf[cnt] = make_uint2(float_to_key(mx), (uint32_t)(col0 + __ffs(above) - 1));
+    ++cnt;
+  }
+  unsigned hm = __ballot_sync(0xffffffffu, n_above > 1);
+  if (hm == 0u) {
+    compact_rows(__ballot_sync(0xffffffffu, cnt > P.cap - 32), P.cap - 64, P, grow, thr, cnt, my_buf, hist, lane);
+    return;
+  }
+  if (n_above > 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
   }
@@ -703,10 +719,10 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   // for uneven placement; QST_KUNIT overrides (kunit = kprime is the most conservative setting).
   {
     // Poisson tail: a stripe holds ~k'/S of the k' best documents; 3x that plus 16 keeps the chance
-    // that a unit's threshold climbs above the k'-th best score negligible (kunit = 16 at 28 stripes
-    // left 56 of 20 000 queries uncertified, kunit = 32 none)
-    int ku = (int)round_up(3 * (int)ceil_div(kprime, plan->stripes) + 16, 8);
-    if (ku < 24) ku = 24;
+    // that a unit's threshold climbs above the k'-th best score negligible (at 28 stripes and
+    // k' = 192, kunit = 16 left 56 of 20 000 queries uncertified, kunit = 32 none)
+    int ku = (int)round_up(3 * (int)ceil_div(kprime, plan->stripes) + 8, 8);
+    if (ku < 16) ku = 16;
     if (ku > kprime) ku = kprime;
     const char* e = getenv("QST_KUNIT");
     if (e && atoi(e) >= 8) { ku = (int)round_up(atoi(e), 8); if (ku > kprime) ku = kprime; }

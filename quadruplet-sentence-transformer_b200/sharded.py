@@ -258,7 +258,7 @@ class ShardedCorpus:
                 # thresholds are shared by the units of ALL shards: size the per-unit retention for
                 # k' of the whole corpus spread over stripes x shards units (same Poisson-tail rule as
                 # qst_topk_plan_make)
-                ku = max(24, -(-(3 * -(-kprime_all // (plan.stripes * G)) + 16) // 8) * 8)
+                ku = max(16, -(-(3 * -(-kprime_all // (plan.stripes * G)) + 8) // 8) * 8)
                 _lib.check(lib.qst_topk_plan_set_kunit(C.byref(plan), min(ku, plan.kunit)))
             ws = scoring._workspace(plan.ws_bytes, dev, "select")
             if hints is not None:

@@ -62,7 +62,7 @@ def test_plan_invariants(lib):
                 assert plan.ctas == int(ctas) and plan.rows_per_unit == 128 * plan.ctas
                 assert plan.D_pad % 64 == 0 and plan.D_pad >= D
                 assert plan.kprime >= k and plan.kprime % 16 == 0
-                assert min(24, plan.kprime) <= plan.kunit <= plan.kprime and plan.cap >= plan.kunit + 64
+                assert min(16, plan.kprime) <= plan.kunit <= plan.kprime and plan.cap >= plan.kunit + 64
                 assert plan.m_tiles * plan.rows_per_unit >= Q > (plan.m_tiles - 1) * plan.rows_per_unit
                 assert plan.n_tiles * 256 >= N > (plan.n_tiles - 1) * 256
                 assert plan.stripes * plan.tiles_per_stripe >= plan.n_tiles
