@@ -295,6 +295,10 @@ def run_ours(args):
     shard = full[n0:n1]
     qgen = torch.Generator(device=dev).manual_seed(14 + 200)
     queries = torch.randn(Q, DIM, generator=qgen, device=dev, dtype=torch.float32)
+    if world > 1:
+        # every rank's host owns its 10 000 queries of the batch (global query id = rank*10000 + i):
+        # only those cross PCIe on this rank; the bf16 operands of the others arrive over NVLink
+        queries = queries[rank * Q_PER_GPU:(rank + 1) * Q_PER_GPU].clone()
     queries_host = queries.cpu().pin_memory()
 
     if world > 1:
@@ -308,7 +312,7 @@ def run_ours(args):
 
     def step_device():
         if corp is not None:
-            return corp.topk(queries, TOPK)
+            return corp.topk_owned(queries, TOPK)
         r = scoring.topk(queries, index, TOPK)
         return r.values, r.indices, r.margin
 
@@ -317,7 +321,7 @@ def run_ours(args):
     def step_host():
         if corp is not None:
             qd = queries_host.to(dev, non_blocking=True)
-            v, i, _ = corp.topk(qd, TOPK)
+            v, i, _ = corp.topk_owned(qd, TOPK)
             if not host_out:   # pinned result buffers are allocated once (cudaHostAlloc costs ms)
                 host_out["v"] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
                 host_out["i"] = torch.empty(i.shape, dtype=i.dtype, pin_memory=True)
@@ -356,7 +360,10 @@ def run_ours(args):
     ms_step, out = timed(step_device, steps)
     clocks = sampler.stop()
     margin = out[2]
-    uncertified = int((margin <= 0).sum())
+    unc = (margin <= 0).sum().to(torch.int64)
+    if world > 1:
+        dist.all_reduce(unc)
+    uncertified = int(unc)
 
     # ---- the dominant kernel alone, on the same stream, inside the same kind of step -----------
     plan = scoring.make_plan(Q, index.n, DIM, TOPK, 0, "cos_sim")

@@ -231,11 +231,40 @@ class ShardedCorpus:
 
     # ---- master="replicated": lists of bf16 candidates go to the owner of each query -----------
     def _topk_candidate_exchange(self, queries, k, kprime, exact):
-        lib = _lib.load()
+        """All queries in, all rankings out (every rank): slices the batch by owner, runs
+        ``topk_owned`` and all-gathers the rankings."""
         dev = self.index.device
         G = self.world
         Q = queries.shape[0]
         q_own = -(-Q // G)
+        q_pad = q_own * G
+        if q_pad != Q:     # pad with copies of the last query so that every rank owns q_own rows
+            queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
+        vals, idx, margin = self.topk_owned(queries[self.rank * q_own:(self.rank + 1) * q_own], k, kprime, exact)
+        with torch.cuda.device(dev):
+            gv, gi = all_gather_topk(vals, idx, self.group)                 # [G, q_own, k]
+            gm = torch.empty(q_pad, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gm, margin, group=self.group)
+            if self._timing:
+                self._mark(self._timing[-1], "all_gather")
+        return gv.view(q_pad, k)[:Q], gi.view(q_pad, k)[:Q], gm[:Q]
+
+    def topk_owned(self, own_queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True):
+        """Collective: every rank passes ITS OWN slice of the query batch (same number of rows on
+        every rank; global query id = rank * rows + i) and gets the exact global top-k of that slice
+        back: (values [q_own, k], global ids [q_own, k], margins [q_own]).
+
+        Only the bf16 tensor-core operands of the queries travel between ranks (one all-gather over
+        NVLink); fp32 queries, rescoring and results stay with the owner.  Needs the replicated
+        fp32 master (``full_master=``).
+        """
+        if self.master is None:
+            raise _lib.QstError("topk_owned needs ShardedCorpus(full_master=...) (candidate exchange)")
+        lib = _lib.load()
+        dev = self.index.device
+        G = self.world
+        own_queries = own_queries.to(dev)
+        q_own = own_queries.shape[0]
         q_pad = q_own * G
         score = self.score
         cos = score == "cos_sim"
@@ -244,16 +273,19 @@ class ShardedCorpus:
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             self._mark(marks, "start")
-            if q_pad != Q:     # pad with copies of the last query so that every rank owns q_own rows
-                queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
-            pq = scoring.prepare_rows(queries, scoring.QUERY_PREP[score])
-            self._mark(marks, "prep")
+            pq = scoring.prepare_rows(own_queries, scoring.QUERY_PREP[score])
+            if G > 1:
+                q_bf16 = torch.empty((q_pad, pq.bf16.shape[1]), dtype=torch.bfloat16, device=dev)
+                dist.all_gather_into_tensor(q_bf16, pq.bf16, group=self.group)
+            else:
+                q_bf16 = pq.bf16
+            self._mark(marks, "prep+gather_q")
             # k' of the whole corpus decides how many candidates every shard lists (m); the shard's
             # own K2 then only has to retain its m best
             kprime_all = scoring.make_plan(q_pad, self.n_total, self.index.d, k, kprime, score).kprime
             m = candidates_per_shard(kprime_all, G)
             plan = scoring.make_plan(q_pad, self.index.n, self.index.d, min(k, m), m, score)
-            hints = self._hints_for(plan.m_tiles * plan.rows_per_unit, dev)
+            hints = self._hints_for(plan.m_tiles * plan.rows_per_unit, dev) if G > 1 else None
             if hints is not None:
                 # thresholds are shared by the units of ALL shards: size the per-unit retention for
                 # k' of the whole corpus spread over stripes x shards units (same Poisson-tail rule as
@@ -263,48 +295,41 @@ class ShardedCorpus:
             ws = scoring._workspace(plan.ws_bytes, dev, "select")
             if hints is not None:
                 local, peers, n_peers = hints.launch_args()
-                _lib.check(lib.qst_score_select_peers(C.byref(plan), pq.bf16.data_ptr(),
+                _lib.check(lib.qst_score_select_peers(C.byref(plan), q_bf16.data_ptr(),
                                                       self.index.rows.bf16.data_ptr(), ws.data_ptr(), local, peers,
                                                       n_peers, st))
                 hints.advance(st)
             else:
-                _lib.check(lib.qst_score_select(C.byref(plan), pq.bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+                _lib.check(lib.qst_score_select(C.byref(plan), q_bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
                                                 ws.data_ptr(), st))
             self._mark(marks, "K2")
             lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
             _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
             self._mark(marks, "select")
-            recv = exchange_candidate_lists(lists, self.group)              # [G, q_own, m+1, 2]
+            recv = exchange_candidate_lists(lists, self.group) if G > 1 else lists.view(1, q_pad, m + 1, 2)
             self._mark(marks, "all_to_all")
-            own = slice(self.rank * q_own, (self.rank + 1) * q_own)
             vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
             margin = torch.empty(q_own, dtype=torch.float32, device=dev)
             scratch = scoring._workspace(lib.qst_finalize_lists_scratch_bytes(q_own, G), dev, "lists")
             mst = self.master
-            q_f32 = pq.f32[own]
-            q_inv = pq.inv_norm[own] if cos else None
-            q_err = pq.err[own]
+            q_inv = pq.inv_norm if cos else None
             _lib.check(lib.qst_finalize_lists(q_own, G, m, k, kprime_all, code, self.index.d, recv.data_ptr(),
-                                              q_f32.data_ptr(), _lib.ptr(q_inv), q_err.data_ptr(),
+                                              pq.f32.data_ptr(), _lib.ptr(q_inv), pq.err.data_ptr(),
                                               mst.f32.data_ptr(), mst.inv_norm.data_ptr() if cos else None,
                                               mst.stats.data_ptr(), vals.data_ptr(), idx.data_ptr(),
                                               margin.data_ptr(), scratch.data_ptr(), st))
             self._mark(marks, "finalize_lists")
             if exact:
                 rs = scoring._workspace(lib.qst_exact_rescan_workspace_bytes(q_own, k), dev, "rescan")
-                _lib.check(lib.qst_exact_rescan(q_own, self.n_total, self.index.d, k, code, q_f32.data_ptr(),
+                _lib.check(lib.qst_exact_rescan(q_own, self.n_total, self.index.d, k, code, pq.f32.data_ptr(),
                                                 _lib.ptr(q_inv), mst.f32.data_ptr(),
                                                 mst.inv_norm.data_ptr() if cos else None, 0, vals.data_ptr(),
                                                 idx.data_ptr(), margin.data_ptr(), rs.data_ptr(), st))
             self._mark(marks, "rescan")
-            gv, gi = all_gather_topk(vals, idx, self.group)                 # [G, q_own, k]
-            gm = torch.empty(q_pad, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(gm, margin, group=self.group)
-            self._mark(marks, "all_gather")
             if marks is not None:
                 self._timing.append(marks)
-        return gv.view(q_pad, k)[:Q], gi.view(q_pad, k)[:Q], gm[:Q]
+        return vals, idx, margin
 
     # ---- master="sharded": exact per-shard top-k lists, all-gather, merge ---------------------------
     def _topk_list_exchange(self, queries, k, kprime, exact):

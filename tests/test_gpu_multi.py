@@ -42,6 +42,16 @@ def _worker(rank, world, port, out_dir):
             # only tie swaps (scores within 1e-6) may differ
             assert float((vals.cpu()[mism] - want_val[mism]).abs().max() if mism.any() else 0.0) <= 2e-6
             assert mism.float().mean() < 1e-3
+            if full is not None:
+                # owner-sliced entry: every rank passes its slice, gets its slice of the answer
+                q_own = -(-Q // world)
+                qp = torch.cat([q, q[-1:].expand(q_own * world - Q, -1)])
+                lo, hi = rank * q_own, (rank + 1) * q_own
+                v2, i2, m2 = corp.topk_owned(qp[lo:hi].to(dev), k)
+                hi_real = min(hi, Q)
+                torch.testing.assert_close(v2.cpu()[: hi_real - lo], want_val[lo:hi_real], rtol=0, atol=2e-6)
+                assert (i2.cpu()[: hi_real - lo] != want_idx[lo:hi_real]).float().mean() < 1e-3
+                assert bool((m2 > 0).all())
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
