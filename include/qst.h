@@ -243,7 +243,9 @@ int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, int score, in
  * every corpus row is scored in fp32 against each flagged query and rows scoring at least the
  * current k-th best are collected, which yields the exact top k regardless of bf16 error.
  * Runs entirely on device (no host read of the flags).  scratch from
- * qst_exact_rescan_workspace_bytes(). */
+ * qst_exact_rescan_workspace_bytes().  One call serves at most 8192 flagged queries (16 per corpus
+ * pass) and collects at most 2048 rows per query; queries beyond those limits keep margin <= 0 and
+ * can be served by calling again. */
 size_t qst_exact_rescan_workspace_bytes(int64_t Q, int k);
 int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score,
                      const float* q_f32, const float* q_inv, const float* c_f32, const float* c_inv,

@@ -400,7 +400,9 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
 //   step 1  rescan_collect:  grid (corpus blocks, flagged-query batches)
 //   step 2  rescan_emit:     one CTA per query
 // ------------------------------------------------------------------------------------------
-constexpr int kRescanCap = 4096;  // collected rows per flagged query (>= k + ties)
+constexpr int kRescanCap = 2048;        // collected rows per flagged query (>= k + ties at the threshold)
+constexpr int kRescanMaxFlagged = 8192; // flagged queries served per call (bounds the scratch to 128 MB);
+                                        // any beyond that keep margin <= 0 and can be served by another call
 
 struct RescanScratch {
   int n_flagged;
@@ -415,10 +417,10 @@ __global__ void rescan_list_kernel(const float* margin, int Q, int* flagged, Res
   for (int base = 0; base < Q; base += blockDim.x) {
     const int q = base + threadIdx.x;
     const bool f = q < Q && !(margin[q] > 0.f);
-    if (f) { const int p = atomicAdd(&s_n, 1); flagged[p] = q; }
+    if (f) { const int p = atomicAdd(&s_n, 1); if (p < kRescanMaxFlagged) flagged[p] = q; }
   }
   __syncthreads();
-  if (threadIdx.x == 0) hdr->n_flagged = s_n;
+  if (threadIdx.x == 0) hdr->n_flagged = s_n < kRescanMaxFlagged ? s_n : kRescanMaxFlagged;
   for (int i = threadIdx.x; i < Q; i += blockDim.x) counts[i] = 0;
 }
 
@@ -653,7 +655,8 @@ extern "C" int qst_merge_topk(const float* vals, const int64_t* idx, int G, int6
 extern "C" size_t qst_exact_rescan_workspace_bytes(int64_t Q, int k) {
   (void)k;
   // header | flagged[Q] | counts[Q] | coll_val[Q*cap] | coll_idx[Q*cap]  (worst case: all flagged)
-  return 256 + round_up((size_t)Q * 4, 256) * 2 + (size_t)Q * kRescanCap * 8;
+  const size_t nf = (size_t)(Q < kRescanMaxFlagged ? Q : kRescanMaxFlagged);
+  return 256 + round_up((size_t)Q * 4, 256) * 2 + nf * kRescanCap * 8;
 }
 
 extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score, const float* q_f32,
@@ -668,7 +671,8 @@ extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int scor
   RescanScratch* hdr = reinterpret_cast<RescanScratch*>(p); p += 256;
   int* flagged = reinterpret_cast<int*>(p); p += round_up((size_t)Q * 4, 256);
   int* counts = reinterpret_cast<int*>(p); p += round_up((size_t)Q * 4, 256);
-  float* coll_val = reinterpret_cast<float*>(p); p += (size_t)Q * kRescanCap * 4;
+  const size_t nf_max = (size_t)(Q < kRescanMaxFlagged ? Q : kRescanMaxFlagged);
+  float* coll_val = reinterpret_cast<float*>(p); p += nf_max * kRescanCap * 4;
   int* coll_idx = reinterpret_cast<int*>(p);
   rescan_list_kernel<<<1, 1024, 0, st>>>(margin_inout, (int)Q, flagged, hdr, counts);
   QST_LAUNCH_CHECK();
