@@ -267,7 +267,14 @@ __device__ __forceinline__ void compact_rows(unsigned need, int max_keep, const 
 // ------------------------------------------------------------------------------------------
 constexpr int kStagePitch = 33;  // floats per staged row: conflict-free for both access patterns
 
-constexpr int kChunkMax = 16;   // running top-16 of a row's per-chunk maxima (count-16 threshold guarantee)
+constexpr int kChunkMax = 20;   // running top-20 of a row's per-chunk maxima (count-20 threshold guarantee)
+
+// sorted (descending) insertion of x into cm[]
+__device__ __forceinline__ void cm_insert(float (&cm)[kChunkMax], float x) {
+#pragma unroll
+  for (int i = kChunkMax - 1; i > 0; --i) cm[i] = x > cm[i - 1] ? cm[i - 1] : fmaxf(cm[i], x);
+  cm[0] = fmaxf(cm[0], x);
+}
 
 template <bool DENSE>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, const ScoreParams& P, int grow, bool row_ok,
@@ -300,17 +307,26 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
   const bool hit = mx > thr;
   if (__ballot_sync(0xffffffffu, hit) == 0u) return;
-  // Running top-16 of this row's per-chunk maxima (sorted registers): 16 distinct documents of this
-  // unit score at least cm[15], so it is a threshold with the same kind of guarantee as a
+  // Running top-20 of this row's per-chunk maxima (sorted registers): 20 distinct documents of this
+  // unit score at least cm[19], so it is a threshold with the same kind of guarantee as a
   // compaction's, but it matures chunk by chunk -- a cold unit does not have to fill and compact
   // its buffer several times to get going.  Takes effect after this chunk's appends.
   float thr_next = thr;
   if (P.chunkmax && hit) {
+    if (thr == -INFINITY) {
+      // stone-cold row (first chunk of a unit, no hint yet): seed with ALL 32 values, so that the
+      // very next chunk is already filtered against the 20th best of these (the lane only touches
+      // its own row of the staging tile here)
 #pragma unroll
-    for (int i = kChunkMax - 1; i > 0; --i) cm[i] = mx > cm[i - 1] ? cm[i - 1] : fmaxf(cm[i], mx);
-    cm[0] = fmaxf(cm[0], mx);
+      for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
+#pragma unroll 1
+      for (int j = 0; j < 32; ++j) cm_insert(cm, stage[lane * kStagePitch + j]);
+    } else {
+      cm_insert(cm, mx);
+    }
     thr_next = fmaxf(thr, cm[kChunkMax - 1]);
   }
+  __syncwarp();
   // Some lane has a score above its threshold.  Which ones: a 32-bit mask per lane (predicated, no
   // branches).  The common case by far is ONE such score in the lane's 32 columns -- it is then the
   // row maximum, and the lane appends it on its own, with no cross-lane traffic at all.  Lanes with
@@ -809,7 +825,7 @@ static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, cons
   P.m_tiles = plan->m_tiles; P.n_tiles = plan->n_tiles; P.stripes = plan->stripes;
   P.tiles_per_stripe = plan->tiles_per_stripe; P.units = plan->units;
   P.kunit = plan->kunit; P.cap = plan->cap;
-  // the count-16 chunk-maximum thresholds are as safe as the buffer's own when a unit is expected to
+  // the count-20 chunk-maximum thresholds are as safe as the buffer's own when a unit is expected to
   // hold at most ~5 of the k' best documents (kunit = 3*lambda + 8 <= 24)
   P.chunkmax = plan->kunit <= 24 ? 1 : 0;
   { const char* e = getenv("QST_CHUNKMAX"); if (e) P.chunkmax = atoi(e) != 0; }
