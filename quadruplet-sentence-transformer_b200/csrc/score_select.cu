@@ -173,14 +173,16 @@ __device__ __forceinline__ bool warp_compact_small(uint2* __restrict__ buf, int 
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  const uint64_t span = (uint64_t)(hi - lo) + 1ull;
+  // bin = floor((key - lo) * 256 / (hi - lo + 1)) evaluated in fp32: rounding is monotone, so the
+  // bin index is non-decreasing in the key, which is all the selection needs
+  const float scale = 256.0f / ((float)(hi - lo) + 1.0f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
   __syncwarp();
   int bin[kSmallCap / 32];
 #pragma unroll
   for (int i = 0; i < kSmallCap / 32; ++i) {
-    bin[i] = (int)(((uint64_t)(e[i].x - lo) << 8) / span);   // monotone in the key, 0..255
+    bin[i] = min(255, (int)((float)(e[i].x - lo) * scale));
     if (lane + 32 * i < n) atomicAdd(&hist[bin[i]], 1);
   }
   __syncwarp();
@@ -210,17 +212,22 @@ __device__ __forceinline__ bool warp_compact_small(uint2* __restrict__ buf, int 
   kept = __shfl_sync(0xffffffffu, kept, src);
   __syncwarp();
   if (kept > max_keep) return false;
-  // smallest key that maps to bin bstar: everything dropped is strictly below it
-  T_out = lo + (uint32_t)((((uint64_t)bstar * span) + 255ull) >> 8);
   const unsigned lt = (1u << lane) - 1u;
   int w = 0;
+  uint32_t tmin = 0xffffffffu;   // smallest kept key: everything dropped is strictly below it
 #pragma unroll
   for (int i = 0; i < kSmallCap / 32; ++i) {
     const bool keep = (lane + 32 * i < n) && (bin[i] >= bstar);
     const unsigned km = __ballot_sync(0xffffffffu, keep);
-    if (keep) buf[w + __popc(km & lt)] = e[i];
+    if (keep) {
+      buf[w + __popc(km & lt)] = e[i];
+      tmin = min(tmin, e[i].x);
+    }
     w += __popc(km);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+  T_out = tmin;
   __syncwarp();
   n_out = w;
   return true;
