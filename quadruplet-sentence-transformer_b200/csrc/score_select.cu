@@ -558,12 +558,12 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // flight while chunk c is filtered (two register buffers, loop unrolled by 2)
         uint32_t va[32], vb[32];
         ptx::tmem_ld_32x32(taddr, va);
-        ptx::tmem_ld_wait();
+        ptx::tmem_ld_wait(va);
 #pragma unroll 1
         for (int chunk = 0; chunk < BN / 32; chunk += 2) {
           ptx::tmem_ld_32x32(taddr + (chunk + 1) * 32, vb);
           epilogue_chunk<DENSE>(va, t * BN + chunk * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm);
-          ptx::tmem_ld_wait();
+          ptx::tmem_ld_wait(vb);
           if (chunk + 2 < BN / 32) {
             ptx::tmem_ld_32x32(taddr + (chunk + 2) * 32, va);
           } else {
@@ -576,7 +576,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
           }
           epilogue_chunk<DENSE>(vb, t * BN + (chunk + 1) * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm);
-          if (chunk + 2 < BN / 32) ptx::tmem_ld_wait();
+          if (chunk + 2 < BN / 32) ptx::tmem_ld_wait(va);
         }
         if (!DENSE && row_ok && thr > pub) {   // thresholds raised by the chunk maxima during this tile
           publish_threshold(P, grow, float_to_key(thr));
@@ -784,8 +784,10 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
     const char* e = getenv("QST_KUNIT");
     if (e && atoi(e) >= 8) { ku = (int)round_up(atoi(e), 8); if (ku > kprime) ku = kprime; }
     plan->kunit = ku;
-    // slack between compactions: at least 128 entries
+    // slack between compactions: at least 128 entries; the whole register-resident compaction
+    // window (256) when the unit keeps few, so that a unit rarely compacts before its end
     plan->cap = 2 * ku > ku + 128 ? 2 * ku : ku + 128;
+    if (ku <= 64 && plan->cap < 256) plan->cap = 256;
   }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
   plan_layout(plan);
@@ -797,6 +799,7 @@ extern "C" int qst_topk_plan_set_kunit(qst_topk_plan* plan, int kunit) {
   QST_CHECK_ARG(kunit >= 8 && kunit <= 2048, "plan_set_kunit: kunit=%d out of range", kunit);
   plan->kunit = (int)round_up(kunit, 8);
   plan->cap = 2 * plan->kunit > plan->kunit + 128 ? 2 * plan->kunit : plan->kunit + 128;
+  if (plan->kunit <= 64 && plan->cap < 256) plan->cap = 256;
   plan_layout(plan);
   return QST_OK;
 }
