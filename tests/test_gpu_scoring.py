@@ -21,9 +21,29 @@ def ctas(request, monkeypatch):
     return request.param
 
 
-def assert_same_ranking(got_idx, got_val, want_idx, want_val, what=""):
-    """Index-for-index equality, except inside groups of reference scores within TIE."""
+def _fp64_scores(q, c, idx, score):
+    """Float64 scores of the listed documents, straight from the definitions (diagnostics)."""
+    qq, cc = q.double(), c.double()[idx.clamp_min(0)]          # [Q, k, D]
+    if score == "cos_sim":
+        return torch.nn.functional.cosine_similarity(qq[:, None, :], cc, dim=2, eps=1e-12)
+    if score == "dot_score":
+        return (qq[:, None, :] * cc).sum(2)
+    return 1 / (1 + (qq[:, None, :] - cc).norm(dim=2))
+
+
+def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=None):
+    """Index-for-index equality, except inside groups of reference scores within TIE.
+    `truth` = (q, c, score) lets a value mismatch say WHICH side disagrees with float64."""
     got_idx, got_val = got_idx.cpu(), got_val.cpu()
+    if truth is not None and not torch.allclose(got_val, want_val, rtol=0, atol=2e-6):
+        q, c, score = truth
+        rows = ((got_val - want_val).abs() > 2e-6).any(dim=1).nonzero().flatten()
+        t_got = _fp64_scores(q[rows], c, got_idx[rows], score)
+        t_want = _fp64_scores(q[rows], c, want_idx[rows], score)
+        raise AssertionError(
+            f"{what}: {rows.numel()} rows differ (first {rows[:10].tolist()}); max |ours - fp64| = "
+            f"{float((got_val[rows].double() - t_got).abs().max()):.3e}, max |oracle - fp64| = "
+            f"{float((want_val[rows].double() - t_want).abs().max()):.3e}")
     torch.testing.assert_close(got_val, want_val, rtol=0, atol=2e-6, msg=lambda m: f"{what} scores: {m}")
     mism = (got_idx != want_idx)
     if not mism.any():
@@ -92,7 +112,8 @@ def test_topk_matches_oracle(Q, N, D, k, score, ctas):
         torch.testing.assert_close(res.values.cpu() / scale, want_val / scale, rtol=0, atol=2e-6)
         assert (res.indices.cpu() == want_idx).float().mean() > 0.999
     else:
-        assert_same_ranking(res.indices, res.values, want_idx, want_val, f"{score} {Q}x{N}x{D} k={k}")
+        assert_same_ranking(res.indices, res.values, want_idx, want_val, f"{score} {Q}x{N}x{D} k={k}",
+                            truth=(q, c, score))
     assert bool((res.margin > 0).all()), "every query must end certified (after the exact re-scan if needed)"
 
 
