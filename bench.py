@@ -257,7 +257,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -446,12 +446,32 @@ def run_ours(args):
             line["loss_config2"] = loss_config2(dev, peaks)
         except Exception as e:  # secondary measurement must never break the headline line
             line["loss_config2"] = {"error": repr(e)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line, but libraries loaded later (NCCL's version banner on
+    some boxes) write to file descriptor 1 directly: keep a private duplicate of the real stdout for
+    the JSON line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
