@@ -15,6 +15,7 @@ Public surface (same names and call signatures as the reference side uses):
   (sentence-transformers 2.2.2, as constructed at ``ir_evauation_script.py:107-123``) and the
   reference's own ``euclidean_score`` (``models/evaluators.py:392-405``)
 * ``QuadrupletEvaluator`` (``models/evaluators.py:130-389``) with its paired distances on the device
+* ``QuadrupletLossEvaluator`` (``models/evaluators.py:34-128``): running mean of the fused loss
 * ``CorpusIndex``, ``topk``: the scoring engine underneath
 * ``ShardedCorpus``: corpus-sharded retrieval over NCCL
 
@@ -28,6 +29,7 @@ from .scoring import (CorpusIndex, TopkResult, cos_sim, dot_score, euclidean_sco
                       topk_host)
 from .ir_evaluator import InformationRetrievalEvaluator, load_ir_evaluation_set
 from .quad_evaluator import QuadrupletEvaluator, SimilarityFunction, paired_distance_counts
+from .loss_evaluator import QuadrupletLossEvaluator, dissimilar_mask, incremental_mean_f32
 from . import metrics, synth
 from .sharded import ShardedCorpus
 
@@ -35,5 +37,6 @@ __all__ = [
     "GammaQuadrupletLoss", "QuadrupletLoss", "gamma_quadruplet_loss", "gamma_quadruplet_loss_and_grads",
     "InformationRetrievalEvaluator", "cos_sim", "dot_score", "euclidean_score", "CorpusIndex", "TopkResult", "topk",
     "topk_host", "prepare_rows", "QuadrupletEvaluator", "SimilarityFunction", "paired_distance_counts",
+    "QuadrupletLossEvaluator", "dissimilar_mask", "incremental_mean_f32",
     "load_ir_evaluation_set", "ShardedCorpus", "metrics", "synth", "QstError", "QstLibraryError",
 ]

@@ -77,3 +77,52 @@ def test_evaluator_protocol_and_csv(tmp_path):
     ev2 = qst_b200.QuadrupletEvaluator.from_input_examples(items, gamma=0.5)
     assert ev2.anchors == ["0", "1"] and ev2.negatives == ["900", "901"] and ev2.positives[0] in ("300", "301")
     assert 0.0 <= ev2(model) <= 1.0
+
+
+@pytest.mark.parametrize("n,batch,use_amp", [(150, 32, False), (64, 64, False), (33, 8, True), (5, 32, False)])
+def test_loss_evaluator_running_mean_and_log(tmp_path, n, batch, use_amp):
+    """QuadrupletLossEvaluator (models/evaluators.py:34-128): per-batch fused losses vs the loss oracle
+    (1e-5 relative), running mean bit-identical to the reference expression on the same batch values,
+    JSON log appended per call."""
+    import json
+    import qst_b200
+    from oracle import loss_eval_oracle
+    D = 96
+    a, p, pp, neg = _quads(n, D, 40 + n)
+    model = qst_b200.synth.TableModel(torch.cat([a, p, pp, neg]).to(_dev()))
+
+    class Example:
+        def __init__(self, texts):
+            self.texts = texts
+
+    dataset = [Example([str(k * n + i) for k in range(4)]) for i in range(n)]
+    loss = qst_b200.GammaQuadrupletLoss(gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5)
+    ev = qst_b200.QuadrupletLossEvaluator(dataset, loss, batch_size=batch, use_amp=use_amp)
+    out = str(tmp_path)
+    got = ev(model, output_path=out, epoch=1, steps=10)
+    want_avg, want_losses = loss_eval_oracle.evaluate(a, p, pp, neg, batch, gamma=0.6, margin_pos_neg=1.0,
+                                                      margin_pos_part=0.5, margin_part_neg=0.5)
+    np.testing.assert_allclose(ev.last_batch_losses, want_losses.numpy(), rtol=1e-5)
+    assert got == float(loss_eval_oracle.running_average(list(torch.from_numpy(ev.last_batch_losses))))
+    assert abs(got - float(want_avg)) <= 1e-5 * abs(float(want_avg))
+    again = ev(model, output_path=out, epoch=2, steps=-1)
+    assert again == got
+    with open(os.path.join(out, "_quadruplet_loss_eval.json")) as fp:
+        log = json.load(fp)
+    assert log == {"epoch": [1, 2], "steps": [10, -1], "average_loss": [got, got]}
+    assert ev(model) == got                      # no output path: nothing written, same value
+
+
+def test_dissimilar_mask_matches_cos_sim_threshold():
+    """Negative-mining filter (dataset/quadruplet_dataset.py:229-234) on the device scorer."""
+    import qst_b200
+    from oracle import ir_oracle
+    g = torch.Generator().manual_seed(5)
+    ref = torch.randn(384, generator=g)
+    cand = torch.cat([ref[None] * 0.5 + 0.1 * torch.randn(10, 384, generator=g), torch.randn(40, 384, generator=g)])
+    mask, scores = qst_b200.dissimilar_mask(ref.to(_dev()), cand.to(_dev()), 0.2)
+    want = ir_oracle.cos_sim(ref, cand)[0]
+    np.testing.assert_allclose(scores.cpu().numpy(), want.numpy(), atol=2e-6)
+    sure = (want - 0.2).abs() > 1e-5
+    assert torch.equal(mask.cpu()[sure], (want <= 0.2)[sure])
+    assert int(mask.sum()) >= 35 and not bool(mask[:10].any())

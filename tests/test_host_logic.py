@@ -148,3 +148,38 @@ def test_ir_evaluation_set_loader_and_quadruplet_evaluator_construction(tmp_path
     assert [m.value for m in qst_b200.SimilarityFunction] == [0, 1, 2, 3]
     with pytest.raises(AssertionError):
         qst_b200.QuadrupletEvaluator(["a"], ["b", "x"], ["c"], ["d"])
+
+
+def test_incremental_mean_matches_reference_tensor_arithmetic():
+    """models/evaluators.py:98 replayed on the host in float32 == the torch expression, bit for bit."""
+    import numpy as np
+    import torch
+    import qst_b200
+    from oracle import loss_eval_oracle
+    g = torch.Generator().manual_seed(14)
+    for n in (0, 1, 2, 7, 100, 1001):
+        losses = (torch.rand(n, generator=g) * 3.0).float()
+        want = loss_eval_oracle.running_average(list(losses))
+        got = qst_b200.incremental_mean_f32(losses.numpy())
+        assert isinstance(got, np.float32)
+        want = float(want) if n else 0.0
+        assert float(got) == want, (n, float(got), want)
+
+
+def test_loss_evaluator_instance_shapes():
+    from importlib import import_module
+    le = import_module("qst_b200.loss_evaluator")
+
+    class Ex:
+        def __init__(self, texts):
+            self.texts = texts
+
+    quad = ["a", "b", "c", "d"]
+    assert le._texts_of(Ex(quad)) == quad
+    assert le._texts_of(tuple(quad)) == quad
+    assert le._texts_of({"reference": "a", "positive": ["b", "x"], "part_positive": "c", "negative": ["d"]}) == quad
+    assert le._texts_of((Ex(quad), 0)) == quad
+    import pytest
+    with pytest.raises(ValueError):
+        le._texts_of(["a", "b", "c"])
+    assert [len(b) for b in le._batches(range(10), 4)] == [4, 4, 2]
