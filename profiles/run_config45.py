@@ -75,10 +75,14 @@ def check_rankings(vals, idx, margin, n_total):
 def compare_sample(own_q, vals, idx, full, n_sample=32):
     sel = torch.linspace(0, own_q.shape[0] - 1, n_sample, device=own_q.device).long()
     bv, bi = brute_force_topk(own_q[sel], full, K)
-    same_ids = int((idx[sel] == bi).all(dim=1).sum())
-    # where ids differ it must be a tie within float rounding between neighbours
+    differ = idx[sel] != bi
+    # where ids differ it must be a swap between scores that agree within float rounding (the two
+    # implementations sum in different orders): the VALUES at those positions still line up
+    tie_ok = ((vals[sel] - bv).abs() <= 2e-6) | ~differ
+    same_ids = int((~differ).all(dim=1).sum())
+    up_to_ties = int(tie_ok.all(dim=1).sum())
     dv = float((vals[sel] - bv).abs().max())
-    return same_ids, n_sample, dv
+    return (same_ids, up_to_ties), n_sample, dv
 
 
 def config4(rank, world, dev):
@@ -110,7 +114,7 @@ def config4(rank, world, dev):
     vals, idx, margin = out
     check_rankings(vals, idx, margin, n)
     same, ns, dv = compare_sample(own_q, vals, idx, full)
-    stat = torch.tensor([same, ns], dtype=torch.int64, device=dev)
+    stat = torch.tensor([same[0], ns, same[1]], dtype=torch.int64, device=dev)
     dist.all_reduce(stat)
     stage = corp.stage_ms()
     res = {"config": 4, "Q": q_own * world, "N": n, "D": D, "k": K, "gpus": world, "ms_per_step": ms,
@@ -118,6 +122,7 @@ def config4(rank, world, dev):
            "tflops_per_gpu": 2.0 * q_own * world * (n1 - n0) * D / (stage.get("K2", ms) * 1e-3) / 1e12,
            "stage_ms_rank0": stage, "all_margins_positive": True,
            "brute_force_sample": {"queries": int(stat[1]), "identical_rankings": int(stat[0]),
+                                  "identical_up_to_ties_within_2e-6": int(stat[2]),
                                   "max_abs_value_diff_rank0": dv}}
     del corp, full, out, vals, idx, margin
     torch.cuda.empty_cache()
@@ -183,10 +188,11 @@ def config5(rank, world, dev):
     # brute-force sample on this rank's first batch
     v, i, _ = corp.topk_owned(own_q[:batch], K)
     same, ns, dv = compare_sample(own_q[:batch], v, i, full)
-    stat = torch.tensor([same, ns], dtype=torch.int64, device=dev)
+    stat = torch.tensor([same[0], ns, same[1]], dtype=torch.int64, device=dev)
     dist.all_reduce(stat)
     if rank == 0:
         res["brute_force_sample"] = {"queries": int(stat[1]), "identical_rankings": int(stat[0]),
+                                  "identical_up_to_ties_within_2e-6": int(stat[2]),
                                      "max_abs_value_diff_rank0": dv}
     return res
 
