@@ -36,14 +36,25 @@ def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=Non
     `truth` = (q, c, score) lets a value mismatch say WHICH side disagrees with float64."""
     got_idx, got_val = got_idx.cpu(), got_val.cpu()
     if truth is not None and not torch.allclose(got_val, want_val, rtol=0, atol=2e-6):
+        # arbitration by float64: the fp32 CPU oracle is only a stand-in for the exact scores.  If OUR
+        # values are off, fail with the evidence; if ours agree with float64 and the oracle's do not
+        # (seen twice in ~100 runs on the GPU boxes' hosts, cause unknown), say so loudly and go on
+        # with the float64 scores of the oracle's own ranking.
         q, c, score = truth
         rows = ((got_val - want_val).abs() > 2e-6).any(dim=1).nonzero().flatten()
         t_got = _fp64_scores(q[rows], c, got_idx[rows], score)
         t_want = _fp64_scores(q[rows], c, want_idx[rows], score)
-        raise AssertionError(
-            f"{what}: {rows.numel()} rows differ (first {rows[:10].tolist()}); max |ours - fp64| = "
-            f"{float((got_val[rows].double() - t_got).abs().max()):.3e}, max |oracle - fp64| = "
-            f"{float((want_val[rows].double() - t_want).abs().max()):.3e}")
+        ours_off = float((got_val[rows].double() - t_got).abs().max())
+        oracle_off = float((want_val[rows].double() - t_want).abs().max())
+        report = (f"{what}: {rows.numel()} rows differ (first {rows[:10].tolist()}); max |ours - fp64| = "
+                  f"{ours_off:.3e}, max |oracle - fp64| = {oracle_off:.3e}")
+        if ours_off > 2e-6 or oracle_off <= 2e-6:
+            raise AssertionError(report)
+        import warnings
+        warnings.warn("CPU ORACLE DISAGREES WITH FLOAT64 (ours agrees): " + report)
+        print("CPU ORACLE DISAGREES WITH FLOAT64 (ours agrees): " + report)
+        want_val = want_val.clone()
+        want_val[rows] = t_want.float()
     torch.testing.assert_close(got_val, want_val, rtol=0, atol=2e-6, msg=lambda m: f"{what} scores: {m}")
     mism = (got_idx != want_idx)
     if not mism.any():
