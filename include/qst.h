@@ -209,6 +209,11 @@ int qst_peer_buffer_destroy(void* dev_ptr);
 int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad,
                     float* out, qst_stream_t stream);
 
+/* Debug aid: per-tile trace of the last qst_score_select run with QST_SCORE_DEBUG bit 32 set
+ * (time stamps in ns, candidate count and threshold of each CTA's first row; 64 slots per CTA,
+ * slot 0 = start of the CTA's first unit, slot 63 = its end).  Host pointers, n <= 160*64. */
+int qst_debug_read_trace(long long* ns, int* cnt, float* thr, int n);
+
 /* K3.  Exact fp32 rescoring of the selected candidates and final ordering.
  *   q_f32 [Q, D], c_f32 [N, D]: fp32 masters; q_inv/c_inv: inverse norms (cos) or NULL (dot).
  *   q_err [Q] and c_stats (2 floats) from qst_prep_rows feed the certificate; either may be NULL

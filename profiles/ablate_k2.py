@@ -19,11 +19,11 @@ del corpus
 pq = scoring.prepare_rows(queries, True)
 lib = _lib.load()
 st = _lib.stream_ptr(dev)
-for ctas in sys.argv[1].split(","):
+for ctas in (sys.argv[1] if len(sys.argv) > 1 else "2").split(","):
     os.environ["QST_SCORE_CTAS"] = ctas
     plan = scoring.make_plan(Q, N, D, K, 0, "cos_sim")
     ws = scoring._workspace(plan.ws_bytes, dev, "select")
-    for dbg in sys.argv[2].split(","):
+    for dbg in (sys.argv[2] if len(sys.argv) > 2 else "0,16,2,1").split(","):
         os.environ["QST_SCORE_DEBUG"] = dbg
         ts = []
         for i in range(5):

@@ -12,7 +12,7 @@ namespace qst {
 
 constexpr int kFinThreads = 256;
 constexpr int kFinWarps = kFinThreads / 32;
-constexpr int kMaxStripes = 128;  // must cover qst_topk_plan_make's s_max
+constexpr int kMaxStripes = 160;  // must cover qst_topk_plan_make's s_max
 
 // ------------------------------------------------------------------------------------------
 // CTA-wide: keep the k largest keys of (keys, idx)[0..n) -> compacted to the front (order
@@ -563,6 +563,10 @@ extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspac
   P.rows_per_unit = plan->rows_per_unit;
   int sm_cap = plan->kprime + plan->cap;
   if (sm_cap < 4096) sm_cap = 4096;
+  // many short stripes (small query batches): room for what every unit may leave per row, so the
+  // gather stays a single parallel pass
+  const int expect = plan->stripes * (plan->kunit + 16);
+  if (sm_cap < expect) sm_cap = expect < 12288 ? expect : 12288;
   P.sm_cap = sm_cap;
   P.thr_hint = reinterpret_cast<const uint32_t*>(ws + plan->off_thr);
   P.unit_cnt = reinterpret_cast<const int*>(ws + plan->off_cnt);
@@ -591,6 +595,8 @@ extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* work
   P.rows_per_unit = plan->rows_per_unit;
   int sm_cap = m + plan->cap;
   if (sm_cap < 4096) sm_cap = 4096;
+  const int expect = plan->stripes * (plan->kunit + 16);
+  if (sm_cap < expect) sm_cap = expect < 12288 ? expect : 12288;
   P.sm_cap = sm_cap;
   P.thr_hint = reinterpret_cast<const uint32_t*>(ws + plan->off_thr);
   P.unit_cnt = reinterpret_cast<const int*>(ws + plan->off_cnt);

@@ -239,6 +239,23 @@ __device__ __forceinline__ void publish_threshold(const ScoreParams& P, int grow
   for (int pr = 0; pr < P.n_peers; ++pr) atomicMax(&P.peer_hint[pr][grow], key);   // remote RED, fire and forget
 }
 
+// One row's compaction, OUT OF LINE on purpose: the selection code is large and rarely runs, and the
+// epilogue has a single warp per scheduler, so every instruction-cache miss on the way through the
+// filter is paid in full -- keeping this out of the filter's code path keeps that path short.
+// Returns (new count << 32) | threshold key.
+__device__ __noinline__ unsigned long long compact_one_row(uint2* bp, int n, int kunit, int max_keep, int cap,
+                                                           int* hist, int lane) {
+  uint32_t T = 0u;
+  int n_new = kunit;
+  // fast: one-pass histogram compaction in registers; exact 4-pass radix select otherwise
+  // (large buffers, or keys the histogram cannot separate)
+  if (!(cap <= kSmallCap && warp_compact_small(bp, n, kunit, max_keep, hist, lane, T, n_new))) {
+    T = warp_select_compact(bp, n, kunit, hist, lane);
+    n_new = kunit;
+  }
+  return ((unsigned long long)(uint32_t)n_new << 32) | T;
+}
+
 // Compacts the candidate buffers of the rows in `need` (one bit per lane) down to ~kunit entries
 // and publishes each row's new threshold to the hint array.
 __device__ __forceinline__ void compact_rows(unsigned need, int max_keep, const ScoreParams& P, int grow, float& thr,
@@ -248,16 +265,10 @@ __device__ __forceinline__ void compact_rows(unsigned need, int max_keep, const 
     need &= need - 1;
     uint2* bp = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r));
     const int n = __shfl_sync(0xffffffffu, cnt, r);
-    uint32_t T = 0u;
-    int n_new = P.kunit;
-    // fast: one-pass histogram compaction in registers; exact 4-pass radix select otherwise
-    // (large buffers, or keys the histogram cannot separate)
-    if (!(P.cap <= kSmallCap && warp_compact_small(bp, n, P.kunit, max_keep, hist, lane, T, n_new))) {
-      T = warp_select_compact(bp, n, P.kunit, hist, lane);
-      n_new = P.kunit;
-    }
+    const unsigned long long res = compact_one_row(bp, n, P.kunit, max_keep, P.cap, hist, lane);
     if (lane == r) {
-      cnt = n_new;
+      const uint32_t T = (uint32_t)res;
+      cnt = (int)(res >> 32);
       thr = fmaxf(thr, key_to_float(T));
       publish_threshold(P, grow, T);
     }
@@ -279,14 +290,64 @@ constexpr int kChunkMax = 20;   // running top-20 of a row's per-chunk maxima (c
 // sorted (descending) insertion of x into cm[]
 __device__ __forceinline__ void cm_insert(float (&cm)[kChunkMax], float x) {
 #pragma unroll
-  for (int i = kChunkMax - 1; i > 0; --i) cm[i] = x > cm[i - 1] ? cm[i - 1] : fmaxf(cm[i], x);
+  for (int i = kChunkMax - 1; i > 0; --i) cm[i] = fmaxf(cm[i], fminf(cm[i - 1], x));   // old cm[i-1]: descending i
   cm[0] = fmaxf(cm[0], x);
+}
+
+// End of a unit: drop every entry of every row that is not above the row's final threshold (most
+// were appended while the threshold was still maturing).  One coalesced load and one store per
+// row; the loads of FOUR rows are issued back to back before any of them is compacted, so a warp's
+// 32 rows cost eight memory latencies instead of 32 dependent round trips.  Rows that still hold
+// more than `max_final` entries afterwards (heavy ties) are returned in the mask and go through the
+// selecting compaction.
+__device__ __forceinline__ unsigned final_filter_rows(unsigned need, int max_final, float thr, int& cnt,
+                                                      uint2* my_buf, int lane) {
+  constexpr int E = kSmallCap / 32;
+  constexpr int B = 4;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned still = 0u;
+  while (need) {
+    int r[B], n[B];
+    uint2* bp[B];
+    uint32_t tkey[B];
+    uint2 e[B][E];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const bool ok = need != 0u;
+      r[b] = ok ? __ffs(need) - 1 : 0;
+      need &= need - 1;   // 0 stays 0
+      bp[b] = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r[b]));
+      n[b] = ok ? __shfl_sync(0xffffffffu, cnt, r[b]) : 0;
+      tkey[b] = float_to_key(__shfl_sync(0xffffffffu, thr, r[b]));
+      if (!ok) r[b] = -1;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const int j = lane + 32 * i;
+        e[b][i] = j < n[b] ? bp[b][j] : make_uint2(0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      int w = 0;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const bool keep = (lane + 32 * i < n[b]) && (e[b][i].x > tkey[b]);
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) bp[b][w + __popc(km & lt)] = e[b][i];
+        w += __popc(km);
+      }
+      if (lane == r[b]) cnt = w;
+      if (r[b] >= 0 && w > max_final) still |= 1u << r[b];
+    }
+  }
+  __syncwarp();
+  return still;
 }
 
 template <bool DENSE>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, const ScoreParams& P, int grow, bool row_ok,
                                                float& thr, int& cnt, uint2* my_buf, float* stage, int* hist, int lane,
-                                               float (&cm)[kChunkMax]) {
+                                               float (&cm)[kChunkMax], bool update_cm) {
   if (P.debug & 2) {  // ablation: TMEM reads only
     if (v[0] == 0x7fc12345u) P.unit_cnt[0] = 1;
     return;
@@ -316,28 +377,22 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   if (__ballot_sync(0xffffffffu, hit) == 0u) return;
   // Running top-20 of this row's per-chunk maxima (sorted registers): 20 distinct documents of this
   // unit score at least cm[19], so it is a threshold with the same kind of guarantee as a
-  // compaction's, but it matures chunk by chunk -- a cold unit does not have to fill and compact
-  // its buffer several times to get going.  Takes effect after this chunk's appends.
+  // compaction's, but it matures chunk by chunk -- a unit does not have to fill and compact its
+  // buffer to get going (a cold unit seeds cm[] from its whole first tile, see the kernel).  Takes
+  // effect after this chunk's appends.
   float thr_next = thr;
-  if (P.chunkmax && hit) {
-    if (thr == -INFINITY) {
-      // stone-cold row (first chunk of a unit, no hint yet): seed with ALL 32 values, so that the
-      // very next chunk is already filtered against the 20th best of these (the lane only touches
-      // its own row of the staging tile here)
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
-#pragma unroll 1
-      for (int j = 0; j < 32; ++j) cm_insert(cm, stage[lane * kStagePitch + j]);
-    } else {
-      cm_insert(cm, mx);
-    }
+  if (P.chunkmax && hit && update_cm) {
+    cm_insert(cm, mx);
     thr_next = fmaxf(thr, cm[kChunkMax - 1]);
   }
   __syncwarp();
   // Some lane has a score above its threshold.  Which ones: a 32-bit mask per lane (predicated, no
-  // branches).  The common case by far is ONE such score in the lane's 32 columns -- it is then the
-  // row maximum, and the lane appends it on its own, with no cross-lane traffic at all.  Lanes with
-  // two or more go through the staged, warp-cooperative path below.
+  // branches).  Every lane then appends its own hits to its own row's buffer: one hit (by far the
+  // common case) is the row maximum and needs nothing else; several hits are read back one by one
+  // from the lane's row of the staging tile (registers cannot be indexed by the bit position).
+  // The stores are 8 bytes per lane to 32 different buffers -- uncoalesced but few, and far cheaper
+  // in instructions than serving the rows cooperatively (the epilogue is issue-bound: one warp per
+  // scheduler).
   unsigned above = 0u;
 #pragma unroll
   for (int j = 0; j < 32; ++j) above |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
@@ -345,52 +400,32 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   if (n_above == 1) {
     my_buf[cnt] = make_uint2(float_to_key(mx), (uint32_t)(col0 + __ffs(above) - 1));
     ++cnt;
-  }
-  unsigned hm = __ballot_sync(0xffffffffu, n_above > 1);
-  if (hm == 0u) {
-    thr = thr_next;
-    compact_rows(__ballot_sync(0xffffffffu, cnt > P.cap - 32), P.cap - 64, P, grow, thr, cnt, my_buf, hist, lane);
-    return;
-  }
-  if (n_above > 1) {
+  } else if (n_above > 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) stage[lane * kStagePitch + j] = __uint_as_float(v[j]);
-  }
-  __syncwarp();
-  const unsigned lt = (1u << lane) - 1u;
-  // four hit rows per trip: the four shuffle/load/ballot chains are independent, which hides their
-  // latency (the epilogue has a single warp per scheduler)
-  while (hm) {
-    int r[4];
-    bool ok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ok[i] = hm != 0u;
-      r[i] = ok[i] ? __ffs(hm) - 1 : 0;
-      hm &= hm - 1;          // 0 stays 0
-    }
-    float thr_r[4], val[4];
-    int cnt_r[4];
-    uint2* buf_r[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      thr_r[i] = __shfl_sync(0xffffffffu, thr, r[i]);
-      cnt_r[i] = __shfl_sync(0xffffffffu, cnt, r[i]);
-      buf_r[i] = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)my_buf, r[i]));
-      val[i] = stage[r[i] * kStagePitch + lane];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool p = ok[i] && (val[i] > thr_r[i]);
-      const unsigned pm = __ballot_sync(0xffffffffu, p);
-      if (p) buf_r[i][cnt_r[i] + __popc(pm & lt)] = make_uint2(float_to_key(val[i]), (uint32_t)(col0 + lane));
-      if (ok[i] && lane == r[i]) cnt += __popc(pm);
+    while (above) {
+      const int j = __ffs(above) - 1;
+      above &= above - 1;
+      my_buf[cnt] = make_uint2(float_to_key(stage[lane * kStagePitch + j]), (uint32_t)(col0 + j));
+      ++cnt;
     }
   }
   __syncwarp();
   thr = thr_next;
   // keep room for the next chunk's worst case (32 appends)
   compact_rows(__ballot_sync(0xffffffffu, cnt > P.cap - 32), P.cap - 64, P, grow, thr, cnt, my_buf, hist, lane);
+}
+
+// debug trace (QST_SCORE_DEBUG & 32): per CTA, per tile of its FIRST unit: globaltimer ns, candidate count
+// and threshold of the CTA's row 0
+constexpr int kTraceTiles = 64;
+__device__ long long g_trace_ns[160 * kTraceTiles];
+__device__ int g_trace_cnt[160 * kTraceTiles];
+__device__ float g_trace_thr[160 * kTraceTiles];
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 template <int CTAS, bool DENSE>
@@ -534,6 +569,8 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       int cnt = 0;
       uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * C::UNIT_ROWS + row_in_unit) * (size_t)P.cap;
       uint32_t next_hint = (!DENSE && row_ok) ? __ldcg(&P.thr_hint[grow]) : 0u;
+      const bool tracing = (P.debug & 32) && u == group && warp == 0 && lane == 0 && blockIdx.x < 160;
+      if (tracing) g_trace_ns[blockIdx.x * kTraceTiles] = globaltimer_ns();
       for (int t = t0; t < t1; ++t) {
         if (!DENSE && row_ok) {
           // thresholds published by other units of this row; the load was issued one tile ago
@@ -554,6 +591,39 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           if (acc == 0) acc_phase ^= 1u;
           continue;
         }
+        // Cold start (first tile of a unit whose rows have no threshold yet, chunk-maximum mode):
+        // pass 1 reads the whole tile once only to find (nearly) every row's 20 best scores (cm[]), so
+        // that pass 2 -- the normal filter below -- appends those instead of most of the tile, and
+        // the next tiles start from a "20th best of 256" threshold.  Without it a cold unit
+        // spends its first three tiles appending and compacting (profiles/small_q_trace.py).
+        bool update_cm = true;
+        if (tracing && t == t0) g_trace_ns[blockIdx.x * kTraceTiles + 40] = globaltimer_ns();
+        if (!DENSE && P.chunkmax && t == t0 &&
+            __ballot_sync(0xffffffffu, row_ok && thr == -INFINITY) != 0u) {
+          uint32_t vc[32];
+#pragma unroll 1
+          for (int chunk = 0; chunk < BN / 32; ++chunk) {
+            ptx::tmem_ld_32x32(taddr + chunk * 32, vc);
+            ptx::tmem_ld_wait(vc);
+            const int col0 = t * BN + chunk * 32;
+            // the chunk's four best (sorted insertion, 2 min/max per step), then those four into
+            // cm[]: 20 of the (up to) 32 documents collected this way score >= cm[19]
+            float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = (col0 + j < P.N) ? __uint_as_float(vc[j]) : -INFINITY;
+              c4[3] = fmaxf(c4[3], fminf(c4[2], x));
+              c4[2] = fmaxf(c4[2], fminf(c4[1], x));
+              c4[1] = fmaxf(c4[1], fminf(c4[0], x));
+              c4[0] = fmaxf(c4[0], x);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cm_insert(cm, c4[i]);
+          }
+          if (row_ok) thr = fmaxf(thr, cm[kChunkMax - 1]);
+          update_cm = false;   // cm[] already holds this tile's documents
+          if (tracing) g_trace_ns[blockIdx.x * kTraceTiles + 41] = globaltimer_ns();
+        }
         // software pipeline over the 8 chunks of 32 columns: the TMEM load of chunk c+1 is in
         // flight while chunk c is filtered (two register buffers, loop unrolled by 2)
         uint32_t va[32], vb[32];
@@ -562,7 +632,8 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll 1
         for (int chunk = 0; chunk < BN / 32; chunk += 2) {
           ptx::tmem_ld_32x32(taddr + (chunk + 1) * 32, vb);
-          epilogue_chunk<DENSE>(va, t * BN + chunk * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm);
+          epilogue_chunk<DENSE>(va, t * BN + chunk * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm,
+                                update_cm);
           ptx::tmem_ld_wait(vb);
           if (chunk + 2 < BN / 32) {
             ptx::tmem_ld_32x32(taddr + (chunk + 2) * 32, va);
@@ -575,12 +646,18 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               else ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
             }
           }
-          epilogue_chunk<DENSE>(vb, t * BN + (chunk + 1) * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm);
+          epilogue_chunk<DENSE>(vb, t * BN + (chunk + 1) * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm,
+                                update_cm);
           if (chunk + 2 < BN / 32) ptx::tmem_ld_wait(va);
         }
         if (!DENSE && row_ok && thr > pub) {   // thresholds raised by the chunk maxima during this tile
           publish_threshold(P, grow, float_to_key(thr));
           pub = thr;
+        }
+        if (tracing && t - t0 + 1 < kTraceTiles) {
+          g_trace_ns[blockIdx.x * kTraceTiles + t - t0 + 1] = globaltimer_ns();
+          g_trace_cnt[blockIdx.x * kTraceTiles + t - t0 + 1] = cnt;
+          g_trace_thr[blockIdx.x * kTraceTiles + t - t0 + 1] = thr;
         }
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
@@ -588,7 +665,10 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (!DENSE) {
         // leave ~kunit entries per row and publish the unit's final threshold: later units of the
         // same rows start from it, and K3 has less to gather
-        compact_rows(__ballot_sync(0xffffffffu, cnt > P.kunit), P.cap, P, grow, thr, cnt, my_buf, hist, lane);
+        unsigned need = __ballot_sync(0xffffffffu, cnt > P.kunit);
+        if (P.cap <= kSmallCap && P.chunkmax) need = final_filter_rows(need, P.kunit + 16, thr, cnt, my_buf, lane);
+        compact_rows(need, P.cap, P, grow, thr, cnt, my_buf, hist, lane);
+        if (tracing) g_trace_ns[blockIdx.x * kTraceTiles + kTraceTiles - 1] = globaltimer_ns();
         P.unit_cnt[(size_t)u * C::UNIT_ROWS + row_in_unit] = cnt;
         P.unit_thr[(size_t)u * C::UNIT_ROWS + row_in_unit] = row_ok ? float_to_key(thr) : 0u;
       }
@@ -685,10 +765,14 @@ static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_
 }
 
 // QST_SCORE_CTAS=1 forces the single-CTA tile (debugging / comparison); default is CTA pairs.
-static int default_ctas() {
+// CTA pairs (M = 256) unless the whole query batch fits one 128-row tile: a pair would then spend
+// half of its tensor time on empty rows, and the pass is corpus-streaming bound (148 independent
+// single-CTA walkers pull more HBM bandwidth than 74 pairs).  QST_SCORE_CTAS=1|2 overrides.
+static int default_ctas(int64_t Q) {
   const char* e = getenv("QST_SCORE_CTAS");
   if (e && e[0] == '1') return 1;
-  return 2;
+  if (e && e[0] == '2') return 2;
+  return Q <= BM ? 1 : 2;
 }
 
 static int device_sm_count() {
@@ -737,7 +821,7 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   plan->Q = Q; plan->N = N; plan->D = D; plan->D_pad = qst_padded_dim_for(D, score == QST_SCORE_EUCLID ? QST_PREP_EUCLID_CORPUS : QST_PREP_RAW);
   plan->k = k; plan->kprime = kprime;
   plan->score = score;
-  plan->ctas = default_ctas();
+  plan->ctas = default_ctas(Q);
   plan->rows_per_unit = BM * plan->ctas;
   plan->m_tiles = (int)ceil_div(Q, plan->rows_per_unit);
   plan->n_tiles = (int)ceil_div(N, BN);
@@ -748,7 +832,7 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   const int r_min = 4;
   int s_max = plan->n_tiles / r_min;
   if (s_max < 1) s_max = 1;
-  if (s_max > 128) s_max = 128;
+  if (s_max > 160) s_max = 160;   // finalize.cu kMaxStripes
   const int64_t tile_bytes = (int64_t)BN * plan->D_pad * 2;
   int64_t r_l2 = (32ll << 20) / tile_bytes;
   if (r_l2 < r_min) r_l2 = r_min;
@@ -853,13 +937,21 @@ static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, cons
   return launch_score(plan->ctas, false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
 }
 
+extern "C" int qst_debug_read_trace(long long* ns, int* cnt, float* thr, int n) {
+  QST_CHECK_ARG(n >= 0 && n <= 160 * kTraceTiles, "debug_read_trace: bad n");
+  QST_CUDA(cudaMemcpyFromSymbol(ns, g_trace_ns, sizeof(long long) * n));
+  QST_CUDA(cudaMemcpyFromSymbol(cnt, g_trace_cnt, sizeof(int) * n));
+  QST_CUDA(cudaMemcpyFromSymbol(thr, g_trace_thr, sizeof(float) * n));
+  return QST_OK;
+}
+
 extern "C" int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad, float* out,
                                qst_stream_t stream) {
   QST_CHECK_ARG(q_bf16 && c_bf16 && out, "score_dense: null argument");
   QST_CHECK_ARG(Q >= 1 && N >= 1 && D_pad >= BK && D_pad % BK == 0, "score_dense: bad shape");
   ScoreParams P{};
   P.Q = (int)Q; P.N = (int)N; P.num_kb = (int)(D_pad / BK);
-  const int ctas = default_ctas();
+  const int ctas = default_ctas(Q);
   P.m_tiles = (int)ceil_div(Q, BM * ctas); P.n_tiles = (int)ceil_div(N, BN);
   P.stripes = 1; P.tiles_per_stripe = P.n_tiles; P.units = P.m_tiles;
   P.dense_out = out;
