@@ -463,3 +463,24 @@ def test_candidate_exchange_emulated_on_one_gpu():
         else:
             assert_same_ranking(idx, vals, want_idx, want_val, f"candidate exchange {score}")
         assert bool((margin > 0).all()), score
+
+
+@pytest.mark.parametrize("Q", [3, 100, 300])
+def test_topk_heavy_ties_small_and_large_batches(Q):
+    """A corpus of 40 distinct rows each repeated 250 times: every score is tied 250-fold, so units end
+    with far more than kunit entries above any threshold (the selecting compaction after the final
+    filter) and the ranking must break ties towards the lower corpus position."""
+    import qst_b200
+    g = torch.Generator().manual_seed(77)
+    base = torch.randn(40, 128, generator=g)
+    c = base.repeat(250, 1)                       # row i = base[i % 40]
+    q = base[torch.arange(Q) % 40] + 0.05 * torch.randn(Q, 128, generator=g)
+    k = 20
+    res = qst_b200.topk(q.to(_dev()), qst_b200.CorpusIndex(c.to(_dev())), k)
+    want_val, _ = _oracle_topk(q, c, k)
+    torch.testing.assert_close(res.values.cpu(), want_val, rtol=0, atol=2e-6)
+    idx = res.indices.cpu()
+    # the 20 best are the 20 lowest positions of the query's own base row: i, i+40, i+80, ...
+    want_idx = (torch.arange(Q) % 40)[:, None] + 40 * torch.arange(k)[None, :]
+    assert torch.equal(idx, want_idx)
+    assert bool((res.margin > 0).all())
