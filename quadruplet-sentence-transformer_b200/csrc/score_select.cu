@@ -768,11 +768,16 @@ static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_
 // CTA pairs (M = 256) unless the whole query batch fits one 128-row tile: a pair would then spend
 // half of its tensor time on empty rows, and the pass is corpus-streaming bound (148 independent
 // single-CTA walkers pull more HBM bandwidth than 74 pairs).  QST_SCORE_CTAS=1|2 overrides.
+// (profiles/small_q_probe.py; for Q = 160..768 the two shapes are otherwise within 2 % of each other)
 static int default_ctas(int64_t Q) {
   const char* e = getenv("QST_SCORE_CTAS");
   if (e && e[0] == '1') return 1;
   if (e && e[0] == '2') return 2;
-  return Q <= BM ? 1 : 2;
+  if (Q <= BM) return 1;
+  // small batches whose last 256-row block would be at most half full (Q = 384: 0.50 ms single
+  // against 0.62 ms in pairs): pairs pad the batch to a multiple of 256 rows, single tiles to 128
+  if (Q <= 2048 && ((Q - 1) % (2 * BM)) < BM) return 1;
+  return 2;
 }
 
 static int device_sm_count() {
