@@ -81,6 +81,25 @@ def test_plan_invariants(lib):
     assert plan.units / (waves * groups) > 0.95
 
 
+def test_plan_picks_tile_shape_and_stripes_for_small_batches(lib):
+    """Without QST_SCORE_CTAS: single-CTA tiles (M=128) when the batch fits one tile or when its last
+    256-row block would be at most half full (small batches only), CTA pairs otherwise; a small batch
+    against a long corpus gets one stripe per CTA (up to 160)."""
+    import qst_b200
+    os.environ.pop("QST_SCORE_CTAS", None)
+    want = {1: 1, 32: 1, 128: 1, 129: 2, 256: 2, 257: 1, 384: 1, 385: 2, 512: 2, 640: 1, 1000: 2, 2048: 2,
+            2049: 2, 2100: 2, 10_000: 2, 100_000: 2}
+    for Q, ctas in want.items():
+        plan = qst_b200._lib.TopkPlan()
+        assert lib.qst_topk_plan_make(Q, 1_000_000, 768, 100, 0, 0, 148, C.byref(plan)) == 0
+        assert plan.ctas == ctas, (Q, plan.ctas, ctas)
+        assert plan.stripes <= 160 and plan.grid <= 148 // plan.ctas
+    plan = qst_b200._lib.TopkPlan()
+    lib.qst_topk_plan_make(128, 1_000_000, 768, 100, 0, 0, 148, C.byref(plan))
+    assert plan.units == plan.stripes >= 140 and plan.grid == plan.units      # one corpus pass, all SMs busy
+    assert plan.kunit == 16 and plan.cap == 256
+
+
 def test_struct_layouts():
     import qst_b200
     assert C.sizeof(qst_b200._lib.QuadParams) == 32
