@@ -170,7 +170,10 @@ typedef struct qst_topk_plan {
 } qst_topk_plan;
 
 /* Fills `plan` for (Q queries, N corpus rows, D dims, top k).  kprime <= 0 picks the default
- * head-room.  sm_count <= 0 queries the current device. */
+ * head-room.  sm_count <= 0 queries the current device.  Tile shape: CTA pairs (256 query rows per
+ * work unit) by default, single-CTA tiles (128 rows) for batches of at most 128 queries and for
+ * batches of at most 2048 whose last 256-row block would be at most half full; the environment
+ * variable QST_SCORE_CTAS=1|2 forces one. */
 int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kprime, int score, int sm_count,
                        qst_topk_plan* plan);
 
