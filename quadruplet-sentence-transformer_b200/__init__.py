@@ -25,8 +25,8 @@ from . import _lib
 from ._lib import QstError, QstLibraryError
 from .quad_loss import (GammaQuadrupletLoss, QuadrupletLoss, gamma_quadruplet_loss,
                         gamma_quadruplet_loss_and_grads)
-from .scoring import (CorpusIndex, TopkResult, cos_sim, dot_score, euclidean_score, prepare_rows, topk,
-                      topk_host)
+from .scoring import (CorpusIndex, HostTopkPipeline, TopkResult, cos_sim, dot_score, euclidean_score, prepare_rows,
+                      topk, topk_host)
 from .ir_evaluator import InformationRetrievalEvaluator, load_ir_evaluation_set
 from .quad_evaluator import QuadrupletEvaluator, SimilarityFunction, paired_distance_counts
 from .loss_evaluator import QuadrupletLossEvaluator, dissimilar_mask, incremental_mean_f32
@@ -36,7 +36,7 @@ from .sharded import ShardedCorpus
 __all__ = [
     "GammaQuadrupletLoss", "QuadrupletLoss", "gamma_quadruplet_loss", "gamma_quadruplet_loss_and_grads",
     "InformationRetrievalEvaluator", "cos_sim", "dot_score", "euclidean_score", "CorpusIndex", "TopkResult", "topk",
-    "topk_host", "prepare_rows", "QuadrupletEvaluator", "SimilarityFunction", "paired_distance_counts",
+    "topk_host", "HostTopkPipeline", "prepare_rows", "QuadrupletEvaluator", "SimilarityFunction", "paired_distance_counts",
     "QuadrupletLossEvaluator", "dissimilar_mask", "incremental_mean_f32",
     "load_ir_evaluation_set", "ShardedCorpus", "metrics", "synth", "QstError", "QstLibraryError",
 ]

@@ -263,3 +263,71 @@ def topk_host(queries_host: torch.Tensor, index: CorpusIndex, k: int, kprime: in
     idx.copy_(res.indices, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     return vals, idx
+
+
+class HostTopkPipeline:
+    """Back-to-back end-to-end calls with HOST buffers, double-buffered.
+
+    ``topk_host`` serialises copy-in, kernels and copy-out of one batch.  A stream of batches (the
+    reference evaluates query sets batch after batch against the same corpus) does not have to:
+    every slot owns a CUDA stream, a pinned result buffer and -- through the per-stream workspace
+    cache -- its own K2 workspace, so the H2D copy of batch i+1 and the D2H copy of batch i-1 run on
+    the copy engines while the kernels of batch i occupy the SMs.  ``submit`` returns at once;
+    ``result`` waits for that batch only.  Per batch the same work is done as in ``topk_host``
+    (pinned queries in, K1, K2, K3, re-scan, pinned ranking out).
+    """
+
+    def __init__(self, index: CorpusIndex, k: int, kprime: int = 0, exact: bool = True, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.index, self.k, self.kprime, self.exact = index, k, kprime, exact
+        dev = index.device
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        for st in self._streams:                         # the index was built on the caller's stream
+            st.wait_stream(torch.cuda.current_stream(dev))
+        self._events = [None] * depth
+        self._out = [None] * depth
+        self._keep = [None] * depth          # device tensors of the batch in flight on a slot
+        self._next = 0
+
+    def submit(self, queries_host: torch.Tensor) -> int:
+        """Queue one batch of pinned host queries; returns the ticket for ``result``."""
+        slot = self._next % len(self._streams)
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()             # the slot's previous batch has fully left
+        dev = self.index.device
+        st = self._streams[slot]
+        with torch.cuda.stream(st):
+            q_dev = queries_host.to(dev, non_blocking=True)
+            res = topk(q_dev, self.index, self.k, self.kprime, self.exact)
+            shape = tuple(res.values.shape)
+            if self._out[slot] is None or tuple(self._out[slot][0].shape) != shape:
+                self._out[slot] = (torch.empty(shape, dtype=torch.float32, pin_memory=True),
+                                   torch.empty(shape, dtype=torch.int64, pin_memory=True))
+            self._out[slot][0].copy_(res.values, non_blocking=True)
+            self._out[slot][1].copy_(res.indices, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._events[slot] = ev
+        self._keep[slot] = (q_dev, res)                  # alive until the slot is reused
+        ticket = self._next
+        self._next += 1
+        return ticket
+
+    def result(self, ticket: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Pinned (values, indices) of a submitted batch; valid until its slot is submitted to again
+        (``depth`` submissions later)."""
+        if not (self._next - len(self._streams) <= ticket < self._next):
+            raise ValueError(f"ticket {ticket} is not in flight (next {self._next}, depth {len(self._streams)})")
+        slot = ticket % len(self._streams)
+        self._events[slot].synchronize()
+        return self._out[slot]
+
+    @property
+    def streams(self):
+        return list(self._streams)
+
+    def drain(self):
+        for ev in self._events:
+            if ev is not None:
+                ev.synchronize()

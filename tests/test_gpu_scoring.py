@@ -484,3 +484,29 @@ def test_topk_heavy_ties_small_and_large_batches(Q):
     want_idx = (torch.arange(Q) % 40)[:, None] + 40 * torch.arange(k)[None, :]
     assert torch.equal(idx, want_idx)
     assert bool((res.margin > 0).all())
+
+
+def test_host_pipeline_matches_synchronous_calls():
+    """HostTopkPipeline: double-buffered host-buffer calls return what topk_host returns, batch by
+    batch, whatever the interleaving of their copies and kernels."""
+    import qst_b200
+    g = torch.Generator().manual_seed(9)
+    c = torch.randn(20_000, 128, generator=g)
+    index = qst_b200.CorpusIndex(c.to(_dev()))
+    batches = [torch.randn(n, 128, generator=g).pin_memory() for n in (300, 300, 1, 700, 300, 300, 129)]
+    want = []
+    for b in batches:
+        v, i = qst_b200.topk_host(b, index, 10)
+        want.append((v.clone(), i.clone()))
+    pipe = qst_b200.HostTopkPipeline(index, 10)
+    tickets = []
+    for n, b in enumerate(batches):
+        tickets.append(pipe.submit(b))
+        if n >= 1:                                   # collect one behind: two batches in flight
+            v, i = pipe.result(tickets[n - 1])
+            assert torch.equal(i, want[n - 1][1]) and torch.equal(v, want[n - 1][0]), n - 1
+    v, i = pipe.result(tickets[-1])
+    assert torch.equal(i, want[-1][1]) and torch.equal(v, want[-1][0])
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])                      # long overwritten
+    pipe.drain()
