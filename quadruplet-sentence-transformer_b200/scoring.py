@@ -164,6 +164,12 @@ class TopkResult:
     plan: _lib.TopkPlan
 
 
+# Query rows per K2 launch.  The candidate workspace grows with the number of query rows (about 100 KB
+# per row at 1M corpus rows); larger batches are walked in tiles of this many rows, which costs
+# nothing (a tile already fills the machine many times over) and bounds the workspace to ~3 GB.
+QUERY_TILE = 32768
+
+
 def topk(queries: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0, exact: bool = True,
          prepared_queries: Optional[PreparedRows] = None) -> TopkResult:
     """Exact top-``k`` corpus rows per query under ``index.score``.
@@ -180,6 +186,18 @@ def topk(queries: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0, exa
     if Q == 0:
         z = torch.empty((0, k), device=dev)
         return TopkResult(z, z.long(), torch.empty(0, device=dev), None)
+    if Q > QUERY_TILE:
+        with torch.cuda.device(dev):
+            vals = torch.empty((Q, k), dtype=torch.float32, device=dev)
+            idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+            margin = torch.empty(Q, dtype=torch.float32, device=dev)
+            for s in range(0, Q, QUERY_TILE):
+                e = min(Q, s + QUERY_TILE)
+                tile = PreparedRows(pq.f32[s:e], pq.bf16[s:e], pq.inv_norm[s:e], pq.sq_norm[s:e], pq.err[s:e],
+                                    pq.stats)
+                r = topk(None, index, k, kprime, exact, prepared_queries=tile)
+                vals[s:e], idx[s:e], margin[s:e] = r.values, r.indices, r.margin
+        return TopkResult(vals, idx, margin, r.plan)
     plan = make_plan(Q, N, D, k, kprime, index.score)
     st = _lib.stream_ptr(dev)
     cos = index.score == "cos_sim"

@@ -510,3 +510,18 @@ def test_host_pipeline_matches_synchronous_calls():
     with pytest.raises(ValueError):
         pipe.result(tickets[0])                      # long overwritten
     pipe.drain()
+
+
+def test_large_query_batches_are_tiled(monkeypatch):
+    """Batches above scoring.QUERY_TILE rows are walked in tiles (bounded workspace): same result."""
+    import qst_b200
+    from qst_b200 import scoring
+    g = torch.Generator().manual_seed(31)
+    q = torch.randn(350, 64, generator=g).to(_dev())
+    index = qst_b200.CorpusIndex(torch.randn(5000, 64, generator=g).to(_dev()), "euclid_score")
+    whole = qst_b200.topk(q, index, 10)
+    monkeypatch.setattr(scoring, "QUERY_TILE", 100)
+    tiled = qst_b200.topk(q, index, 10)
+    assert tiled.plan.Q == 50                         # the last tile's plan: 350 = 3 * 100 + 50
+    assert torch.equal(tiled.indices, whole.indices) and torch.equal(tiled.values, whole.values)
+    assert bool((tiled.margin > 0).all())
