@@ -182,8 +182,16 @@ class InformationRetrievalEvaluator:
             out = {}
             prepared_q = {}
             partial = {fn: [] for fn in self.score_functions}
-            for start in range(0, n_corpus, self.corpus_chunk_size):
-                end = min(start + self.corpus_chunk_size, n_corpus)
+            # corpus_chunk_size bounds the reference's [Q, chunk] score matrix; nothing like it exists
+            # here, so embeddings that already sit on the device are scored in one pass (the union of
+            # per-chunk top-k lists is the same set; one pass rescoring k' rows per query instead of
+            # k' per chunk), up to a bf16 operand of 16 GB per pass
+            chunk = self.corpus_chunk_size
+            if corpus_embeddings is not None and corpus_embeddings.is_cuda and n_corpus > chunk:
+                rows_16gb = max(1, (16 << 30) // (2 * max(64, corpus_embeddings.shape[1])))
+                chunk = max(chunk, min(n_corpus, rows_16gb))
+            for start in range(0, n_corpus, chunk):
+                end = min(start + chunk, n_corpus)
                 if corpus_embeddings is None:
                     sub = self._encode(corpus_model, self.corpus[start:end], dev)
                 else:

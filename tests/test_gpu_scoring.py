@@ -525,3 +525,24 @@ def test_large_query_batches_are_tiled(monkeypatch):
     assert tiled.plan.Q == 50                         # the last tile's plan: 350 = 3 * 100 + 50
     assert torch.equal(tiled.indices, whole.indices) and torch.equal(tiled.values, whole.values)
     assert bool((tiled.margin > 0).all())
+
+
+def test_evaluator_scores_device_resident_corpus_in_one_pass():
+    """corpus_embeddings already on the device: one pass over the corpus instead of corpus_chunk_size
+    chunks + merge -- identical metrics and rankings."""
+    import qst_b200
+    q, c, queries, corpus, relevant = qst_b200.synth.ir_eval_set(300, 5000, 96)
+    table = torch.cat([q, c]).to(_dev())
+    model = qst_b200.synth.TableModel(table)
+    kw = dict(corpus_chunk_size=700, mrr_at_k=[10], ndcg_at_k=[10], accuracy_at_k=[1, 10],
+              precision_recall_at_k=[1, 10], map_at_k=[100], write_csv=False)
+    ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
+        "cos_sim": qst_b200.cos_sim, "euclid_score": qst_b200.euclidean_score}, **kw)
+    chunked = ev.rank(model)                                             # encodes chunk by chunk, merges 8 lists
+    one_pass = ev.rank(model, corpus_embeddings=table[300:])            # resident: a single K2/K3 pass
+    for fn in chunked:
+        assert torch.equal(chunked[fn].indices, one_pass[fn].indices), fn
+        assert torch.equal(chunked[fn].values, one_pass[fn].values), fn
+    assert ev.compute_metrices(model) == ev.compute_metrices(model, corpus_embeddings=table[300:])
+    host = ev.rank(model, corpus_embeddings=table[300:].cpu())          # host embeddings: chunked copies, same result
+    assert all(torch.equal(host[fn].indices, chunked[fn].indices) for fn in chunked)
