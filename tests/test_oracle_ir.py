@@ -113,3 +113,39 @@ def test_csv_layout(tmp_path):
     assert lines[0].split(",")[:4] == ["epoch", "steps", "cos_sim-Accuracy@1", "cos_sim-Precision@1"]
     assert "dot_score-MAP@100" == lines[0].split(",")[-1]
     assert len(lines) == 3 and lines[1].startswith("1,2,") and lines[2].startswith("1,3,")
+
+
+def test_metrics_against_independent_implementations():
+    """The IR half of the oracle has no reference fixture to pin it (sentence-transformers 2.2.2 is not
+    available), so its metric loops are cross-checked against independent code: scikit-learn's
+    ``ndcg_score`` (same log2 discount; binary gains; ideal ranking over the whole corpus) and
+    closed-form numpy expressions for MRR / MAP / precision / recall / accuracy on full rankings
+    without ties."""
+    from sklearn.metrics import ndcg_score
+    rng = np.random.default_rng(14)
+    n_q, n_c, ks = 40, 60, [1, 3, 10, 25]
+    queries = {f"q{i}": str(i) for i in range(n_q)}
+    corpus = {f"d{j}": str(j) for j in range(n_c)}
+    scores = rng.permuted(np.tile(np.linspace(0.0, 1.0, n_c), (n_q, 1)), axis=1)      # no ties
+    relevant = {f"q{i}": {f"d{j}" for j in rng.choice(n_c, size=int(rng.integers(1, 9)), replace=False)}
+                for i in range(n_q)}
+    ev = io.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, mrr_at_k=ks, ndcg_at_k=ks,
+                                                accuracy_at_k=ks, precision_recall_at_k=ks, map_at_k=ks,
+                                                write_csv=False)
+    hits = [[{"corpus_id": f"d{j}", "score": float(scores[i, j])} for j in range(n_c)] for i in range(n_q)]
+    got = ev.compute_metrics(hits)
+    y_true = np.array([[1.0 if f"d{j}" in relevant[f"q{i}"] else 0.0 for j in range(n_c)] for i in range(n_q)])
+    order = np.argsort(-scores, axis=1)
+    rel_sorted = np.take_along_axis(y_true, order, axis=1)                              # [q, rank]
+    n_rel = y_true.sum(1)
+    for k in ks:
+        assert math.isclose(got["ndcg@k"][k], ndcg_score(y_true, scores, k=k), rel_tol=1e-12)
+        top = rel_sorted[:, :k]
+        assert math.isclose(got["accuracy@k"][k], float((top.sum(1) > 0).mean()), rel_tol=1e-12)
+        assert math.isclose(got["precision@k"][k], float((top.sum(1) / k).mean()), rel_tol=1e-12)
+        assert math.isclose(got["recall@k"][k], float((top.sum(1) / n_rel).mean()), rel_tol=1e-12)
+        first = np.where(top.any(1), top.argmax(1) + 1, np.inf)
+        assert math.isclose(got["mrr@k"][k], float((1.0 / first).mean()), rel_tol=1e-12)
+        prec_at_hit = np.cumsum(top, axis=1) / np.arange(1, top.shape[1] + 1)
+        ap = (prec_at_hit * top).sum(1) / np.minimum(k, n_rel)
+        assert math.isclose(got["map@k"][k], float(ap.mean()), rel_tol=1e-12)
