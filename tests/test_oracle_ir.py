@@ -149,3 +149,25 @@ def test_metrics_against_independent_implementations():
         prec_at_hit = np.cumsum(top, axis=1) / np.arange(1, top.shape[1] + 1)
         ap = (prec_at_hit * top).sum(1) / np.minimum(k, n_rel)
         assert math.isclose(got["map@k"][k], float(ap.mean()), rel_tol=1e-12)
+
+
+def test_scores_and_topk_against_independent_implementations():
+    """Score functions and the top-k of the oracle against scikit-learn / numpy in float64."""
+    from sklearn.metrics.pairwise import cosine_similarity, euclidean_distances
+    g = torch.Generator().manual_seed(14)
+    q = torch.randn(50, 96, generator=g)
+    c = torch.randn(400, 96, generator=g) * (0.5 + torch.rand(400, 1, generator=g))
+    q64, c64 = q.double().numpy(), c.double().numpy()
+    truth = {"cos_sim": cosine_similarity(q64, c64), "dot_score": q64 @ c64.T,
+             "euclid_score": 1.0 / (1.0 + euclidean_distances(q64, c64))}
+    fns = {"cos_sim": io.cos_sim, "dot_score": io.dot_score, "euclid_score": io.euclidean_score}
+    for name, want in truth.items():
+        got = fns[name](q, c).double().numpy()
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 2e-6 * max(1.0, scale), name
+        vals, idx = io.topk_dense(q, c, 10, name, corpus_chunk_size=150)
+        order = np.argsort(-want, axis=1, kind="stable")[:, :10]
+        gap = np.take_along_axis(want, np.argsort(-want, axis=1)[:, :11], axis=1)
+        clear = (gap[:, :-1] - gap[:, 1:]).min(1) > 1e-5 * max(1.0, scale)       # rows without near-ties
+        assert clear.sum() > 25
+        assert np.array_equal(idx.numpy()[clear], order[clear]), name
