@@ -167,6 +167,8 @@ typedef struct qst_topk_plan {
   int32_t ctas, rows_per_unit;   /* CTAs per tile (2 = cta_group::2 pairs), query rows per work unit */
   size_t ws_bytes;
   size_t off_thr, off_cnt, off_uthr, off_cand; /* layout inside the workspace */
+  int32_t qs;                    /* 1: query-stationary kernel (query block resident in TMEM; CTA pairs, D_pad <= 768) */
+  int32_t reserved_;
 } qst_topk_plan;
 
 /* Fills `plan` for (Q queries, N corpus rows, D dims, top k).  kprime <= 0 picks the default
@@ -247,18 +249,56 @@ int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, int score, in
                        const float* c_inv, const float* c_stats, float* out_val, int64_t* out_idx,
                        float* out_margin, void* scratch, qst_stream_t stream);
 
+/* ---- corpus-sharded retrieval, fp32 master SHARDED too (each GPU keeps its shard
+ * only).  After qst_select_candidates on every shard and ONE exchange of the lists (as above):
+ *   owner :  qst_select_requests   the k' best candidates overall by bf16 key, grouped by the shard that
+ *                                   holds them: out_req [G, Q, m] int32 row ids LOCAL to shard g (-1 = none),
+ *                                   out_bound [Q] = bf16 key bounding every document that is not requested;
+ *                                   scratch: qst_finalize_lists_scratch_bytes(Q, G).  Shards are the balanced
+ *                                   contiguous ranges of n_total rows (first n_total % G shards one row longer).
+ *            -- exchange: block g of out_req goes to shard g --
+ *   shard :  qst_rescore_requests  exact fp32 scores of the requested rows from the shard's OWN fp32 rows:
+ *                                   req [rows, m] (rows = G owners x Q queries, as received), q_f32 [rows, D]
+ *                                   the all-gathered fp32 queries in the same order, out [rows, m] fp32
+ *                                   (cos_sim / dot_score: the score; euclid_score: ||q-c||^2; -inf where req < 0)
+ *            -- exchange back: block o of out goes to owner o --
+ *   owner :  qst_finalize_exact    orders the exact scores (ties: lower global id), emits top k + certificate
+ *                                   exactly as qst_finalize_topk does; exact [G, Q, m] as received, req the
+ *                                   array qst_select_requests wrote; c_stats = max over shards of the two
+ *                                   statistics of qst_prep_rows. */
+int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
+                        int32_t* out_req, uint32_t* out_bound, void* scratch, qst_stream_t stream);
+int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
+                         const float* q_inv, const float* c_f32, const float* c_inv, float* out,
+                         qst_stream_t stream);
+int qst_finalize_exact(int64_t Q, int G, int m, int k, int score, int64_t D, int64_t n_total,
+                       const int32_t* req, const float* exact, const uint32_t* bound, const float* q_f32,
+                       const float* q_err, const float* c_stats, float* out_val, int64_t* out_idx,
+                       float* out_margin, qst_stream_t stream);
+
 /* Exact fp32 brute-force re-scan for the queries whose certificate failed (margin <= 0):
  * every corpus row is scored in fp32 against each flagged query and rows scoring at least the
  * current k-th best are collected, which yields the exact top k regardless of bf16 error.
  * Runs entirely on device (no host read of the flags).  scratch from
- * qst_exact_rescan_workspace_bytes().  One call serves at most 8192 flagged queries (16 per corpus
- * pass) and collects at most 2048 rows per query; queries beyond those limits keep margin <= 0 and
- * can be served by calling again. */
+ * qst_exact_rescan_workspace_bytes().  A pass serves at most 8192 flagged queries (16 per corpus pass);
+ * the call queues ceil(Q / 8192) passes so that every flagged query is served (a pass with nothing left
+ * to do is three empty launches).  At most 2048 rows are collected per query: a query with more than
+ * 2048 rows tied at or above its k-th score cannot be repaired and is left with margin == 0 exactly --
+ * the only way a query can come out of this call uncertified. */
 size_t qst_exact_rescan_workspace_bytes(int64_t Q, int k);
 int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score,
                      const float* q_f32, const float* q_inv, const float* c_f32, const float* c_inv,
                      int64_t idx_offset, float* out_val, int64_t* out_idx, float* margin_inout,
                      void* scratch, qst_stream_t stream);
+/* The same scan on ONE SHARD of a sharded corpus: for every flagged query (margin[q] < 0; margins are not
+ * modified) the shard's rows scoring at least kth_val[q] (the owner's current k-th exact score) are
+ * written as a descending list padded with (-inf, -1) to out_val / out_idx [Q, k]; rows of unflagged
+ * queries are left untouched.  Merging the G shards' lists (qst_merge_topk) gives the exact top k.
+ * overflow [Q] (or NULL): 1 where more than 2048 rows of this shard qualified. */
+int qst_exact_rescan_lists(int64_t Q, int64_t N, int64_t D, int k, int score,
+                           const float* q_f32, const float* q_inv, const float* c_f32, const float* c_inv,
+                           int64_t idx_offset, const float* kth_val, const float* margin,
+                           float* out_val, int64_t* out_idx, int* overflow, void* scratch, qst_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K6  merge of per-shard top-k lists (after the NCCL all-gather of SURVEY.md section 8e).

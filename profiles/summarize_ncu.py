@@ -1,6 +1,6 @@
 """Turn an .ncu-rep (read here on the CPU box with `ncu -i`) into a small committed summary.
 
-    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_xxx.json [algorithmic_flop] [algorithmic_bytes]
+    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r02_xxx.json [algorithmic_flop] [algorithmic_bytes]
 """
 import csv
 import io
@@ -18,7 +18,21 @@ KEYS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
     "sm__cycles_elapsed.avg.per_second", "smsp__inst_executed.sum",
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
+    "sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu_realtime.avg.pct_of_peak_sustained_elapsed",
+    "lts__lts2xbar_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
+
+
+def key_of(header: str):
+    """The raw page prefixes some metrics with their section ("TPC.TriageCompute.sm__pipe_tensor_..."):
+    match the metric name by SUFFIX, so those land in the summary under their plain name."""
+    for k in KEYS:
+        if header == k or header.endswith("." + k):
+            return k
+    return None
 
 
 def main():
@@ -32,8 +46,10 @@ def main():
     for r in rows[2:]:
         d = {}
         for i, h in enumerate(hdr):
-            if h in ("Kernel Name", "ID") or h in KEYS:
-                d[h] = r[i] + ((" " + units[i]) if units[i] and h not in ("Kernel Name", "ID") else "")
+            k = h if h in ("Kernel Name", "ID") else key_of(h)
+            if k is None or (k in d and not r[i]):
+                continue
+            d[k] = r[i] + ((" " + units[i]) if units[i] and k not in ("Kernel Name", "ID") else "")
         launches.append(d)
     summary = {"report": rep, "launches": launches}
     # per-launch DRAM traffic (bytes) of the first profiled launch, for bench.py's roofline.traffic

@@ -43,7 +43,7 @@ class TopkPlan(C.Structure):
                 ("grid", C.c_int32), ("score", C.c_int32),
                 ("ctas", C.c_int32), ("rows_per_unit", C.c_int32),
                 ("ws_bytes", C.c_size_t), ("off_thr", C.c_size_t), ("off_cnt", C.c_size_t), ("off_uthr", C.c_size_t),
-                ("off_cand", C.c_size_t)]
+                ("off_cand", C.c_size_t), ("qs", C.c_int32), ("reserved_", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -81,6 +81,10 @@ SIGNATURES = {
     "qst_finalize_lists_scratch_bytes": (C.c_size_t, [_I64, _INT]),
     "qst_finalize_lists": (_INT, [_I64, _INT, _INT, _INT, _INT, _INT, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, _P]),
+    "qst_select_requests": (_INT, [_I64, _INT, _INT, _INT, _I64, _P, _P, _P, _P, _P]),
+    "qst_rescore_requests": (_INT, [_I64, _INT, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),
+    "qst_finalize_exact": (_INT, [_I64, _INT, _INT, _INT, _INT, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "qst_exact_rescan_lists": (_INT, [_I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "qst_exact_rescan_workspace_bytes": (C.c_size_t, [_I64, _INT]),
     "qst_exact_rescan": (_INT, [_I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "qst_merge_topk": (_INT, [_P, _P, _INT, _I64, _INT, _P, _P, _P]),

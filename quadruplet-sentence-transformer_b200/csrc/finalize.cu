@@ -181,7 +181,28 @@ struct FinParams {
   // select-only mode (sharded retrieval, step 1): write the m best candidates by bf16 key instead
   // of rescoring; entry m of each row carries (bound key, count)
   uint2* sel_out;
+  // request mode (fully sharded master, owner side): instead of rescoring, the k' best candidates are
+  // grouped by the shard that holds them: req_out [G, Q, req_m] local row ids (-1 = none),
+  // bound_out [Q] = bf16 key bounding everything that is NOT requested
+  int32_t* req_out;
+  uint32_t* bound_out;
+  int req_G, req_m;
+  int64_t n_total;
 };
+
+// balanced contiguous shards (sharded.shard_bounds): first n % G shards hold one row more
+__device__ __forceinline__ int shard_of_row(int64_t id, int64_t n_total, int G, int64_t* start) {
+  const int64_t base = n_total / G, rem = n_total % G;
+  const int64_t big = rem * (base + 1);
+  int g;
+  if (id < big) { g = (int)(id / (base + 1)); *start = (int64_t)g * (base + 1); }
+  else { g = (int)(rem + (id - big) / (base > 0 ? base : 1)); *start = big + (int64_t)(g - rem) * base; }
+  return g;
+}
+__device__ __forceinline__ int64_t shard_start_of(int g, int64_t n_total, int G) {
+  const int64_t base = n_total / G, rem = n_total % G;
+  return (int64_t)g * base + (g < rem ? g : rem);
+}
 
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P) {
   extern __shared__ uint8_t fsm[];
@@ -283,6 +304,25 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
     for (int i = tid; i < P.kprime; i += kFinThreads)
       dst[i] = i < ncand ? make_uint2(keys[i], (uint32_t)((int64_t)idx[i] + P.idx_offset)) : make_uint2(0u, 0xffffffffu);
     if (tid == 0) dst[P.kprime] = make_uint2(bound, (uint32_t)ncand);
+    return;
+  }
+  if (P.req_out) {
+    // hand every selected candidate to the shard that owns its row; slot order inside a shard's list
+    // is arbitrary (the final ordering happens after the exact scores are back)
+    int* s_slot = hist;   // G <= 256 counters
+    for (int g = tid; g < P.req_G; g += kFinThreads) s_slot[g] = 0;
+    for (int g = 0; g < P.req_G; ++g)
+      for (int j = tid; j < P.req_m; j += kFinThreads) P.req_out[((size_t)g * P.Q + q) * P.req_m + j] = -1;
+    __syncthreads();
+    for (int i = tid; i < ncand; i += kFinThreads) {
+      int64_t start;
+      const int64_t id = (int64_t)(uint32_t)idx[i];
+      const int g = shard_of_row(id, P.n_total, P.req_G, &start);
+      const int slot = atomicAdd(&s_slot[g], 1);
+      // a shard listed at most req_m candidates, so its slots cannot overflow
+      if (slot < P.req_m) P.req_out[((size_t)g * P.Q + q) * P.req_m + slot] = (int32_t)(id - start);
+    }
+    if (tid == 0) P.bound_out[q] = reduced ? max(T, Tstar) : Tstar;
     return;
   }
   // every document that is NOT rescored below has a bf16 score <= t_bf
@@ -410,13 +450,16 @@ struct RescanScratch {
 };
 
 __global__ void rescan_list_kernel(const float* margin, int Q, int* flagged, RescanScratch* hdr, int* counts) {
-  // single CTA: ordered list of flagged queries
+  // single CTA: list of the flagged queries (at most kRescanMaxFlagged; a query this pass repairs
+  // gets margin = +inf, so the next pass of qst_exact_rescan lists the ones left over)
   __shared__ int s_n;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   for (int base = 0; base < Q; base += blockDim.x) {
     const int q = base + threadIdx.x;
-    const bool f = q < Q && !(margin[q] > 0.f);
+    // margin == 0 exactly is the "cannot be repaired" mark of rescan_emit_kernel (more than
+    // kRescanCap rows tie at the k-th score): not listed again
+    const bool f = q < Q && !(margin[q] > 0.f) && margin[q] != 0.f;
     if (f) { const int p = atomicAdd(&s_n, 1); if (p < kRescanMaxFlagged) flagged[p] = q; }
   }
   __syncthreads();
@@ -424,15 +467,17 @@ __global__ void rescan_list_kernel(const float* margin, int Q, int* flagged, Res
   for (int i = threadIdx.x; i < Q; i += blockDim.x) counts[i] = 0;
 }
 
-constexpr int kRescanBatch = 16;   // flagged queries scored per corpus pass (register accumulators)
+constexpr int kRescanBatch = 16;   // most flagged queries scored per corpus pass (register accumulators)
 
 // One corpus pass per batch of kRescanBatch flagged queries: the batch's query rows sit in shared
 // memory, every warp streams corpus rows (each row read once per batch) and keeps one accumulator
 // per query.  The per-query operation order is exactly warp_dot_f32's, so scores are bit-identical
 // to the ones K3 produced for the same (query, row).
+template <int kRescanBatch>
 __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k, int score, const float* __restrict__ q_f32,
                                                              const float* __restrict__ q_inv, const float* __restrict__ c_f32,
-                                                             const float* __restrict__ c_inv, const float* __restrict__ cur_val,
+                                                             const float* __restrict__ c_inv, const float* __restrict__ thr_base,
+                                                             int thr_stride, int thr_off,
                                                              const int* __restrict__ flagged, const RescanScratch* hdr,
                                                              int* counts, float* coll_val, int* coll_idx) {
   extern __shared__ float s_q[];  // [kRescanBatch][D]
@@ -453,7 +498,7 @@ __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k
       const int b = threadIdx.x;
       const int q = b < nb ? flagged[f0 + b] : 0;
       s_qid[b] = q;
-      s_thr[b] = b < nb ? cur_val[(size_t)q * k + (k - 1)] : INFINITY;  // exact k-th best so far
+      s_thr[b] = b < nb ? thr_base[(size_t)q * thr_stride + thr_off] : INFINITY;  // exact k-th best so far
       s_qi[b] = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
     }
     __syncthreads();
@@ -508,7 +553,8 @@ __global__ void __launch_bounds__(256) rescan_collect_kernel(int N, int D, int k
 __global__ void __launch_bounds__(kFinThreads) rescan_emit_kernel(int k, int64_t idx_offset, const int* __restrict__ flagged,
                                                                   const RescanScratch* hdr, const int* __restrict__ counts,
                                                                   float* coll_val, int* coll_idx, float* out_val,
-                                                                  int64_t* out_idx, float* margin) {
+                                                                  int64_t* out_idx, float* margin, int partial,
+                                                                  int* overflow) {
   __shared__ float sc[kRescanCap];
   __shared__ int32_t ix[kRescanCap];
   const int nf = hdr->n_flagged;
@@ -524,7 +570,15 @@ __global__ void __launch_bounds__(kFinThreads) rescan_emit_kernel(int k, int64_t
       ix[i] = i < n ? coll_idx[(size_t)f * kRescanCap + i] : -1;
     }
     block_bitonic_sort(sc, ix, n2);
-    if (n >= k) {
+    if (partial) {
+      // one SHARD of a sharded corpus: emit whatever this shard holds at or above the threshold
+      // (possibly fewer than k rows), padded; the owner of the query merges the shards' lists
+      for (int j = threadIdx.x; j < k; j += kFinThreads) {
+        out_val[(size_t)q * k + j] = j < n ? sc[j] : -INFINITY;
+        out_idx[(size_t)q * k + j] = j < n ? (int64_t)ix[j] + idx_offset : (int64_t)-1;
+      }
+      if (threadIdx.x == 0 && overflow) overflow[q] = counts[q] > kRescanCap ? 1 : 0;
+    } else if (n >= k) {
       for (int j = threadIdx.x; j < k; j += kFinThreads) {
         out_val[(size_t)q * k + j] = sc[j];
         out_idx[(size_t)q * k + j] = (int64_t)ix[j] + idx_offset;
@@ -533,6 +587,144 @@ __global__ void __launch_bounds__(kFinThreads) rescan_emit_kernel(int k, int64_t
       if (threadIdx.x == 0) margin[q] = counts[q] <= kRescanCap ? INFINITY : 0.f;
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fully sharded fp32 master (every GPU keeps ITS shard only).
+//   shard side : rescore_requests_kernel  -- exact fp32 scores of the rows an owner asked for, from the
+//                                            shard's own fp32 rows and the all-gathered fp32 queries
+//   owner side : finalize_exact_kernel    -- order the exact scores that came back, emit top k + margin
+// Scores are produced by warp_dot_f32 / apply_score exactly as K3 does, so a ranking is bit-identical
+// to the single-GPU one.  euclid_score: the shard returns ||q-c||^2 and the owner applies
+// 1/(1+sqrt(.)) (it needs the squared distance of the k-th document for the certificate).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFinThreads) rescore_requests_kernel(int m, int D, int score, const int32_t* __restrict__ req,
+                                                                       const float* __restrict__ q_f32,
+                                                                       const float* __restrict__ q_inv,
+                                                                       const float* __restrict__ c_f32,
+                                                                       const float* __restrict__ c_inv, float* __restrict__ out) {
+  extern __shared__ float rq_row[];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += kFinThreads) rq_row[i] = q_f32[(size_t)q * D + i];
+  __syncthreads();
+  const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
+  const bool vec4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(c_f32) & 15u) == 0);
+  const bool sq = score == QST_SCORE_EUCLID;
+  const int32_t* rq = req + (size_t)q * m;
+  float* o = out + (size_t)q * m;
+  for (int j = warp; j < m; j += 2 * kFinWarps) {
+    const int j1 = j + kFinWarps;
+    const int r0 = rq[j];
+    const int r1 = j1 < m ? rq[j1] : -1;
+    if (r0 >= 0 && r1 >= 0) {
+      float d0, d1;
+      if (sq) warp_dot_f32_x2<true>(rq_row, c_f32 + (size_t)r0 * D, c_f32 + (size_t)r1 * D, D, vec4, lane, d0, d1);
+      else warp_dot_f32_x2<false>(rq_row, c_f32 + (size_t)r0 * D, c_f32 + (size_t)r1 * D, D, vec4, lane, d0, d1);
+      if (lane == 0) {
+        o[j] = sq ? d0 : apply_score(d0, score, qi, c_inv, r0);
+        o[j1] = sq ? d1 : apply_score(d1, score, qi, c_inv, r1);
+      }
+    } else {
+      if (r0 >= 0) {
+        const float d0 = sq ? warp_dot_f32<true>(rq_row, c_f32 + (size_t)r0 * D, D, vec4, lane)
+                            : warp_dot_f32<false>(rq_row, c_f32 + (size_t)r0 * D, D, vec4, lane);
+        if (lane == 0) o[j] = sq ? d0 : apply_score(d0, score, qi, c_inv, r0);
+      } else if (lane == 0) {
+        o[j] = -INFINITY;
+      }
+      if (j1 < m) {
+        if (r1 >= 0) {
+          const float d1 = sq ? warp_dot_f32<true>(rq_row, c_f32 + (size_t)r1 * D, D, vec4, lane)
+                              : warp_dot_f32<false>(rq_row, c_f32 + (size_t)r1 * D, D, vec4, lane);
+          if (lane == 0) o[j1] = sq ? d1 : apply_score(d1, score, qi, c_inv, r1);
+        } else if (lane == 0) {
+          o[j1] = -INFINITY;
+        }
+      }
+    }
+  }
+}
+
+constexpr int kExactMax = 2048;   // entries one query can get back (k' <= 2048)
+
+__global__ void __launch_bounds__(kFinThreads) finalize_exact_kernel(int Q, int G, int m, int k, int score, int D, int64_t n_total,
+                                                                     const int32_t* __restrict__ req,
+                                                                     const float* __restrict__ exact_in,
+                                                                     const uint32_t* __restrict__ bound,
+                                                                     const float* __restrict__ q_f32,
+                                                                     const float* __restrict__ q_err,
+                                                                     const float* __restrict__ c_stats, float* out_val,
+                                                                     int64_t* out_idx, float* out_margin) {
+  __shared__ float sc[kExactMax];
+  __shared__ int32_t ix[kExactMax];
+  __shared__ float raw[kExactMax];     // euclid: squared distances in arrival order
+  __shared__ int32_t raw_id[kExactMax];
+  __shared__ int s_n;
+  __shared__ float s_red[kFinWarps];
+  __shared__ float s_kth_d2;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool sq = score == QST_SCORE_EUCLID;
+  if (tid == 0) s_n = 0;
+  float qq = 0.f;
+  for (int i = tid; i < D; i += kFinThreads) { const float v = q_f32[(size_t)q * D + i]; qq = fmaf(v, v, qq); }
+  qq = warp_sum(qq);
+  if (lane == 0) s_red[warp] = qq;
+  __syncthreads();
+  float qnorm2 = 0.f;
+  for (int w = 0; w < kFinWarps; ++w) qnorm2 += s_red[w];
+  for (int e = tid; e < G * m; e += kFinThreads) {
+    const int g = e / m, j = e - g * m;
+    const size_t at = ((size_t)g * Q + q) * m + j;
+    const int32_t r = req[at];
+    if (r < 0) continue;
+    const int p = atomicAdd(&s_n, 1);
+    if (p < kExactMax) {
+      const float x = exact_in[at];
+      const int32_t id = (int32_t)(shard_start_of(g, n_total, G) + r);
+      sc[p] = sq ? 1.0f / (1.0f + sqrtf(x)) : x;
+      ix[p] = id;
+      if (sq) { raw[p] = x; raw_id[p] = id; }
+    }
+  }
+  __syncthreads();
+  const int n = s_n < kExactMax ? s_n : kExactMax;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + tid; i < n2; i += kFinThreads) { sc[i] = -INFINITY; ix[i] = -1; }
+  block_bitonic_sort(sc, ix, n2);
+  for (int j = tid; j < k; j += kFinThreads) {
+    const bool ok = j < n;
+    out_val[(size_t)q * k + j] = ok ? sc[j] : -INFINITY;
+    out_idx[(size_t)q * k + j] = ok ? (int64_t)ix[j] : (int64_t)-1;
+  }
+  if (out_margin) {
+    if (sq && n >= k) {
+      const int32_t want = ix[k - 1];
+      for (int i = tid; i < n; i += kFinThreads)
+        if (raw_id[i] == want) s_kth_d2 = raw[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float t_bf = key_to_float(bound[q]);
+      float margin = INFINITY;
+      if (n >= k && t_bf > -INFINITY) {
+        const float kth = sq ? qnorm2 - s_kth_d2 : sc[k - 1];
+        float eps = 0.f;
+        if (q_err && c_stats) {   // same bound as finalize_kernel
+          const float eq = q_err[q], ec = c_stats[0], cn = c_stats[1];
+          float qn = sqrtf(qnorm2);
+          if (score == QST_SCORE_COS) qn = qnorm2 > 0.f ? 1.0f : 0.f;
+          if (sq) qn *= 2.0f;
+          eps = eq * cn + qn * ec + eq * ec + (float)D * 1.2e-7f * (qn * cn + (sq ? cn * cn : 0.f));
+          if (sq) eps += 1e-5f * cn * cn;
+        }
+        margin = kth - (t_bf + eps);
+      }
+      out_margin[q] = margin;
+    }
   }
 }
 
@@ -648,6 +840,66 @@ extern "C" int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, in
 
 extern "C" size_t qst_finalize_lists_scratch_bytes(int64_t Q, int G) { return (size_t)G * Q * 8; }
 
+extern "C" int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
+                                   int32_t* out_req, uint32_t* out_bound, void* scratch, qst_stream_t stream) {
+  QST_CHECK_ARG(lists && out_req && out_bound && scratch, "select_requests: null argument");
+  QST_CHECK_ARG(Q >= 1 && G >= 1 && G <= kMaxStripes && m >= 1 && kprime >= 1 && kprime <= 2048 && n_total >= G,
+                "select_requests: bad shape Q=%lld G=%d m=%d kprime=%d n_total=%lld", (long long)Q, G, m, kprime,
+                (long long)n_total);
+  QST_CHECK_ARG(n_total < (1ll << 31), "select_requests: corpus ids must fit in 31 bits");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint32_t* thr = reinterpret_cast<uint32_t*>(scratch);
+  int* cnt = reinterpret_cast<int*>(thr + (size_t)G * Q);
+  unpack_list_trailers_kernel<<<(unsigned)ceil_div((int64_t)G * Q, 256), 256, 0, st>>>(
+      reinterpret_cast<const uint2*>(lists), (int64_t)G * Q, m, thr, cnt);
+  QST_LAUNCH_CHECK();
+  FinParams P{};
+  P.Q = (int)Q; P.N = 0; P.D = 0;
+  P.k = kprime; P.kprime = kprime; P.cap = m + 1;
+  P.m_tiles = 1; P.stripes = G; P.score = QST_SCORE_DOT; P.rows_per_unit = (int)Q;
+  int sm_cap = kprime + m + 1;
+  if (sm_cap < G * m) sm_cap = G * m;
+  if (sm_cap < 4096) sm_cap = 4096;
+  if (sm_cap > 16384) sm_cap = 16384;
+  P.sm_cap = sm_cap;
+  P.unit_cnt = cnt; P.unit_thr = thr; P.unit_cand = reinterpret_cast<const uint2*>(lists);
+  P.req_out = out_req; P.bound_out = out_bound; P.req_G = G; P.req_m = m; P.n_total = n_total;
+  const size_t smem = (size_t)sm_cap * 8 + (size_t)kprime * 8 + 16;
+  QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<<<(unsigned)Q, kFinThreads, smem, st>>>(P);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
+                                    const float* q_inv, const float* c_f32, const float* c_inv, float* out,
+                                    qst_stream_t stream) {
+  QST_CHECK_ARG(req && q_f32 && c_f32 && out, "rescore_requests: null argument");
+  QST_CHECK_ARG(rows >= 1 && m >= 1 && D >= 1 && D * 4 <= 200 * 1024, "rescore_requests: bad shape rows=%lld m=%d D=%lld",
+                (long long)rows, m, (long long)D);
+  QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "rescore_requests: unknown score %d", score);
+  QST_CHECK_ARG(score != QST_SCORE_COS || (q_inv && c_inv), "rescore_requests: cos score needs inverse norms");
+  const size_t smem = round_up((size_t)D * 4, 16);
+  QST_CUDA(cudaFuncSetAttribute(rescore_requests_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rescore_requests_kernel<<<(unsigned)rows, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" int qst_finalize_exact(int64_t Q, int G, int m, int k, int score, int64_t D, int64_t n_total,
+                                  const int32_t* req, const float* exact, const uint32_t* bound, const float* q_f32,
+                                  const float* q_err, const float* c_stats, float* out_val, int64_t* out_idx,
+                                  float* out_margin, qst_stream_t stream) {
+  QST_CHECK_ARG(req && exact && bound && q_f32 && out_val && out_idx, "finalize_exact: null argument");
+  QST_CHECK_ARG(Q >= 1 && G >= 1 && m >= 1 && k >= 1 && D >= 1, "finalize_exact: bad shape");
+  QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "finalize_exact: unknown score %d", score);
+  finalize_exact_kernel<<<(unsigned)Q, kFinThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (int)Q, G, m, k, score, (int)D, n_total, req, exact, bound, q_f32, q_err, c_stats, out_val, out_idx, out_margin);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
 extern "C" int qst_merge_topk(const float* vals, const int64_t* idx, int G, int64_t Q, int k, float* out_val,
                               int64_t* out_idx, qst_stream_t stream) {
   QST_CHECK_ARG(vals && idx && out_val && out_idx, "merge_topk: null argument");
@@ -665,13 +917,17 @@ extern "C" size_t qst_exact_rescan_workspace_bytes(int64_t Q, int k) {
   return 256 + round_up((size_t)Q * 4, 256) * 2 + nf * kRescanCap * 8;
 }
 
-extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score, const float* q_f32,
-                                const float* q_inv, const float* c_f32, const float* c_inv, int64_t idx_offset,
-                                float* out_val, int64_t* out_idx, float* margin_inout, void* scratch,
-                                qst_stream_t stream) {
+static int exact_rescan_impl(int64_t Q, int64_t N, int64_t D, int k, int score, const float* q_f32,
+                             const float* q_inv, const float* c_f32, const float* c_inv, int64_t idx_offset,
+                             float* out_val, int64_t* out_idx, float* margin_inout, void* scratch,
+                             const float* thr_base, int thr_stride, int thr_off, int partial, int* overflow,
+                             qst_stream_t stream) {
   QST_CHECK_ARG(q_f32 && c_f32 && out_val && out_idx && margin_inout && scratch, "exact_rescan: null argument");
   QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "exact_rescan: unknown score %d", score);
-  QST_CHECK_ARG((size_t)kRescanBatch * D * 4 <= 200 * 1024, "exact_rescan: D too large");
+  // query rows of one batch live in shared memory: 16 per corpus pass up to D = 3200, fewer beyond
+  int batch = kRescanBatch;
+  while (batch > 1 && (size_t)batch * D * 4 > 200 * 1024) batch >>= 1;
+  QST_CHECK_ARG((size_t)batch * D * 4 <= 200 * 1024, "exact_rescan: D=%lld too large", (long long)D);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
   RescanScratch* hdr = reinterpret_cast<RescanScratch*>(p); p += 256;
@@ -680,20 +936,56 @@ extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int scor
   const size_t nf_max = (size_t)(Q < kRescanMaxFlagged ? Q : kRescanMaxFlagged);
   float* coll_val = reinterpret_cast<float*>(p); p += nf_max * kRescanCap * 4;
   int* coll_idx = reinterpret_cast<int*>(p);
-  rescan_list_kernel<<<1, 1024, 0, st>>>(margin_inout, (int)Q, flagged, hdr, counts);
-  QST_LAUNCH_CHECK();
-  const size_t smem = (size_t)kRescanBatch * D * 4;
-  QST_CUDA(cudaFuncSetAttribute(rescan_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // the flagged list is consumed on the device (no host read of n_flagged): with nothing flagged
-  // every CTA returns at once
+  const size_t smem = (size_t)batch * D * 4;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = sms * 2;
-  rescan_collect_kernel<<<grid, 256, smem, st>>>((int)N, (int)D, k, score, q_f32, q_inv, c_f32, c_inv, out_val, flagged,
-                                                 hdr, counts, coll_val, coll_idx);
-  QST_LAUNCH_CHECK();
-  rescan_emit_kernel<<<(unsigned)(Q < 1024 ? Q : 1024), kFinThreads, 0, st>>>(k, idx_offset, flagged, hdr, counts, coll_val,
-                                                                              coll_idx, out_val, out_idx, margin_inout);
-  QST_LAUNCH_CHECK();
+  // One pass serves at most kRescanMaxFlagged queries (that bounds the scratch); the flagged list is
+  // consumed on the device (no host read of its length), so enough passes are queued to serve EVERY
+  // query even if all of them are flagged -- a pass that finds nothing listed returns at once
+  // (three empty launches).  After the last pass the only queries left with margin <= 0 are those
+  // with more than kRescanCap rows tied at their k-th score (margin == 0).
+  const int passes = (int)ceil_div(Q, kRescanMaxFlagged);
+  for (int pass = 0; pass < passes; ++pass) {
+    rescan_list_kernel<<<1, 1024, 0, st>>>(margin_inout, (int)Q, flagged, hdr, counts);
+    QST_LAUNCH_CHECK();
+#define QST_RESCAN_COLLECT(B)                                                                                          \
+  do {                                                                                                                 \
+    QST_CUDA(cudaFuncSetAttribute(rescan_collect_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    rescan_collect_kernel<B><<<grid, 256, smem, st>>>((int)N, (int)D, k, score, q_f32, q_inv, c_f32, c_inv, thr_base,  \
+                                                      thr_stride, thr_off, flagged, hdr, counts, coll_val, coll_idx);  \
+  } while (0)
+    switch (batch) {
+      case 16: QST_RESCAN_COLLECT(16); break;
+      case 8: QST_RESCAN_COLLECT(8); break;
+      case 4: QST_RESCAN_COLLECT(4); break;
+      case 2: QST_RESCAN_COLLECT(2); break;
+      default: QST_RESCAN_COLLECT(1); break;
+    }
+#undef QST_RESCAN_COLLECT
+    QST_LAUNCH_CHECK();
+    rescan_emit_kernel<<<(unsigned)(Q < 1024 ? Q : 1024), kFinThreads, 0, st>>>(k, idx_offset, flagged, hdr, counts,
+                                                                                coll_val, coll_idx, out_val, out_idx,
+                                                                                margin_inout, partial, overflow);
+    QST_LAUNCH_CHECK();
+    if (partial) break;   // the margins are not updated in this mode: one pass (at most 8192 flagged queries)
+  }
   return QST_OK;
+}
+
+extern "C" int qst_exact_rescan(int64_t Q, int64_t N, int64_t D, int k, int score, const float* q_f32,
+                                const float* q_inv, const float* c_f32, const float* c_inv, int64_t idx_offset,
+                                float* out_val, int64_t* out_idx, float* margin_inout, void* scratch,
+                                qst_stream_t stream) {
+  return exact_rescan_impl(Q, N, D, k, score, q_f32, q_inv, c_f32, c_inv, idx_offset, out_val, out_idx, margin_inout,
+                           scratch, out_val, k, k - 1, 0, nullptr, stream);
+}
+
+extern "C" int qst_exact_rescan_lists(int64_t Q, int64_t N, int64_t D, int k, int score, const float* q_f32,
+                                      const float* q_inv, const float* c_f32, const float* c_inv, int64_t idx_offset,
+                                      const float* kth_val, const float* margin, float* out_val, int64_t* out_idx,
+                                      int* overflow, void* scratch, qst_stream_t stream) {
+  QST_CHECK_ARG(kth_val && margin, "exact_rescan_lists: null argument");
+  return exact_rescan_impl(Q, N, D, k, score, q_f32, q_inv, c_f32, c_inv, idx_offset, out_val, out_idx,
+                           const_cast<float*>(margin), scratch, kth_val, 1, 0, 1, overflow, stream);
 }

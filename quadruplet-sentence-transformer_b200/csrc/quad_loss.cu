@@ -523,6 +523,8 @@ static void launch_vec(const QuadArgs& a, int pm, bool vec_ok, int grid, cudaStr
   else launch_pm<T, 1, KIND>(a, pm, grid, st);
 }
 
+__global__ void fill_scalar_kernel(float* out, float v) { *out = v; }
+
 static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
   QST_CHECK_ARG(a.B >= 0 && a.D >= 1, "quadruplet: bad shape B=%lld D=%lld", (long long)a.B, (long long)a.D);
   QST_CHECK_ARG(dtype == QST_F32 || dtype == QST_F16 || dtype == QST_BF16, "quadruplet: bad dtype %d", dtype);
@@ -532,8 +534,9 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
   if (a.B == 0) {
     if (kind != K_BWD && a.reduction != QST_RED_NONE) {
       // sum over nothing = 0, mean over nothing = nan (torch semantics)
-      const float v = a.reduction == QST_RED_MEAN ? NAN : 0.f;
-      QST_CUDA(cudaMemcpyAsync(a.loss_out, &v, sizeof(float), cudaMemcpyHostToDevice, st));
+      // written by a kernel (not a host-to-device copy of a stack variable): capturable in a CUDA graph
+      fill_scalar_kernel<<<1, 1, 0, st>>>(a.loss_out, a.reduction == QST_RED_MEAN ? NAN : 0.f);
+      QST_LAUNCH_CHECK();
     }
     return QST_OK;
   }
@@ -558,12 +561,15 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
   if (reg_path) {
     // exactly one resident wave of CTAs (3 per SM at <= 168 registers), each looping over rows:
     // fewer partials and tickets in the cross-CTA reduction, no ragged last wave
-    static int sms = 0;
+    // SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs)
+    static int sms_of[64] = {0};
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) sms = sms_of[dev];
     if (sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (sms <= 0) sms = 148;
+      if (dev >= 0 && dev < 64) sms_of[dev] = sms;
     }
     if (grid > sms * 3) grid = sms * 3;
     if (dtype == QST_F32) launch_fused_reg<float>(a, pm, grid, st);

@@ -47,7 +47,7 @@ constexpr int MAX_STAGES = 6;
 
 template <int CTAS>
 struct Cfg {
-  static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int STAGES = CTAS == 1 ? 4 : 6;                // even: the two producer warps take one parity each
   static constexpr int B_ROWS = BN / CTAS;                 // corpus rows staged by one CTA per tile
   static constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
@@ -71,6 +71,9 @@ struct ScoreParams {
   int n_peers;
   int chunkmax;        // 1: rows also raise their threshold from the running top-16 chunk maxima
   int debug;           // QST_SCORE_DEBUG ablation bits (0 in production), see launch_score()
+  // query-stationary kernel: the bf16 query operand as plain rows (it is copied into TMEM, not TMA-staged)
+  const uint4* q_rows; // [Q, D_pad] bf16 viewed as 16-byte vectors
+  int q_pitch16;       // D_pad / 8
 };
 
 // ------------------------------------------------------------------------------------------
@@ -449,7 +452,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // Role -> warp id.  The SM's warp arbiter favours higher warp ids, so the two single-thread
   // roles that feed the tensor pipe (TMA producer, MMA issuer) sit ABOVE the four epilogue warps
   // and are never queued behind their filtering code.
-  constexpr int kWarpTma = 4, kWarpMma = 5, kWarpAlloc = 6;   // warps 0-3: epilogue, warp 7: spare
+  constexpr int kWarpTma = 4, kWarpMma = 5, kWarpAlloc = 6, kWarpTma2 = 7;   // warps 0-3: epilogue
   const uint32_t rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;   // 0 = pair leader
   const int group = blockIdx.x / CTAS, n_groups = gridDim.x / CTAS;
   // 128B swizzle needs 1024-byte aligned stage bases
@@ -479,8 +482,15 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  if (warp == kWarpTma && lane == 0) {
-    // ============================== TMA producer ==============================
+  if (warp == kWarpTma || warp == kWarpTma2) {
+    // ============================== TMA producers =============================
+    // TWO producer threads, one per stage parity (STAGES is even).  A thread needs ~380 cycles for
+    // wait + expect_tx + the first box and ~140 for the second (profiles/ubench_umma.cu: the cost is
+    // the issuing thread's own latency chain, it scales with the number of issuing threads), i.e.
+    // ~580 cycles per k-block against 512 cycles of MMA work: a single producer cannot keep the
+    // tensor pipe fed (QST_SCORE_DEBUG=9: 7.7 ms of feed alone for 8 ms of MMA work).
+    const uint32_t my_parity = warp == kWarpTma ? 0u : 1u;
+    const bool one_producer = (P.debug & 64) != 0;   // ablation: the r01 single producer
     uint32_t stage = 0, phase = 0;
     for (int u = group; u < P.units; u += n_groups) {
       const int s = u / P.m_tiles, m = u - s * P.m_tiles;
@@ -490,29 +500,38 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int t = t0; t < t1; ++t) {
         const int c_row = (P.debug & 4) ? 0 : t * BN + (int)rank * C::B_ROWS;
         for (int kb = 0; kb < P.num_kb; ++kb) {
-          ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
-          const uint32_t full = ptx::smem_u32(&s_full[stage]);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          // queries are re-read by every corpus tile (keep in L2); a corpus tile is re-read by the
-          // other query tiles walking the same stripe (normal priority)
-          if (CTAS == 1) {
-            ptx::mbar_arrive_expect_tx(full, STAGE_BYTES);
-            ptx::tma_load_2d(sa, &tmap_q, full, kb * BK, q_row, ptx::kEvictLast);
-            ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full, kb * BK, c_row, ptx::kEvictNormal);
-          } else {
-            // both CTAs' bytes are accounted on the leader's barrier, which the MMA thread waits on
-            if (rank == 0) ptx::mbar_arrive_expect_tx(full, STAGE_BYTES * 2);
-            const uint32_t leader_full = ptx::mapa_shared(full, 0);
-            ptx::tma_load_2d_pair(sa, &tmap_q, leader_full, kb * BK, q_row, ptx::kEvictLast);
-            ptx::tma_load_2d_pair(sa + A_BYTES, &tmap_c, leader_full, kb * BK, c_row, ptx::kEvictNormal);
+          if (one_producer ? (my_parity != 0u) : ((stage & 1u) != my_parity)) {
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
           }
+          ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
+          if (ptx::elect_one_sync()) {   // whole warp runs the loop, one lane issues
+            const uint32_t full = ptx::smem_u32(&s_full[stage]);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            // queries are re-read by every corpus tile (keep in L2); a corpus tile is re-read by the
+            // other query tiles walking the same stripe (normal priority)
+            if (CTAS == 1) {
+              ptx::mbar_arrive_expect_tx(full, STAGE_BYTES);
+              ptx::tma_load_2d(sa, &tmap_q, full, kb * BK, q_row, ptx::kEvictLast);
+              ptx::tma_load_2d(sa + A_BYTES, &tmap_c, full, kb * BK, c_row, ptx::kEvictNormal);
+            } else {
+              // both CTAs' bytes are accounted on the leader's barrier, which the MMA thread waits on
+              if (rank == 0) ptx::mbar_arrive_expect_tx(full, STAGE_BYTES * 2);
+              const uint32_t leader_full = ptx::mapa_shared(full, 0);
+              ptx::tma_load_2d_pair(sa, &tmap_q, leader_full, kb * BK, q_row, ptx::kEvictLast);
+              ptx::tma_load_2d_pair(sa + A_BYTES, &tmap_c, leader_full, kb * BK, c_row, ptx::kEvictNormal);
+            }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == kWarpMma && lane == 0 && rank == 0) {
-    // ============================== MMA issuer ================================
+  } else if (warp == kWarpMma && rank == 0) {
+    // ============================== MMA issuer (whole warp, one lane issues) ================================
     constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * CTAS, BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
+    const bool quarter_mmas = (P.debug & 8) != 0;                      // ablation: one MMA per k-block
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int u = group; u < P.units; u += n_groups) {
       const int s = u / P.m_tiles;
@@ -521,29 +540,41 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(ptx::smem_u32(&s_tmem_empty[acc]), acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_u + acc * BN;
         for (int kb = 0; kb < P.num_kb; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
           ptx::tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
-          const uint64_t db = ptx::make_sw128_kmajor_desc(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the addr>>4 field
-            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-            if ((P.debug & 8) && k != 0) continue;
-            if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
-            else ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+          if (ptx::elect_one_sync()) {
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+            const uint64_t db = ptx::make_sw128_kmajor_desc(sa + A_BYTES);
+            const uint32_t first = kb != 0 ? 1u : 0u;
+            // four K steps: +32 bytes (16 bf16) inside the 128-byte swizzle row = +2 in the addr>>4 field
+            if (CTAS == 2) {
+              ptx::umma_bf16_pair(d_tmem, da, db, idesc, first);
+              if (!quarter_mmas) {
+                ptx::umma_bf16_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+                ptx::umma_bf16_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+                ptx::umma_bf16_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+              }
+              // frees the smem slot (in both CTAs) once the MMAs that read it have retired
+              ptx::umma_commit_pair(ptx::smem_u32(&s_empty[stage]), 3);
+              // last k-block: accumulator ready for the epilogue warps (of both CTAs)
+              if (kb + 1 == P.num_kb) ptx::umma_commit_pair(ptx::smem_u32(&s_tmem_full[acc]), 3);
+            } else {
+              ptx::umma_bf16(d_tmem, da, db, idesc, first);
+              if (!quarter_mmas) {
+                ptx::umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+                ptx::umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                ptx::umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+              }
+              ptx::umma_commit(ptx::smem_u32(&s_empty[stage]));
+              if (kb + 1 == P.num_kb) ptx::umma_commit(ptx::smem_u32(&s_tmem_full[acc]));
+            }
           }
-          // frees the smem slot (in both CTAs) once the MMAs that read it have retired
-          if (CTAS == 2) ptx::umma_commit_pair(ptx::smem_u32(&s_empty[stage]), 3);
-          else ptx::umma_commit(ptx::smem_u32(&s_empty[stage]));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        // accumulator ready for the epilogue warps (of both CTAs)
-        if (CTAS == 2) ptx::umma_commit_pair(ptx::smem_u32(&s_tmem_full[acc]), 3);
-        else ptx::umma_commit(ptx::smem_u32(&s_tmem_full[acc]));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -571,12 +602,14 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       uint32_t next_hint = (!DENSE && row_ok) ? __ldcg(&P.thr_hint[grow]) : 0u;
       const bool tracing = (P.debug & 32) && u == group && warp == 0 && lane == 0 && blockIdx.x < 160;
       if (tracing) g_trace_ns[blockIdx.x * kTraceTiles] = globaltimer_ns();
+      bool unit_cold = false;
       for (int t = t0; t < t1; ++t) {
         if (!DENSE && row_ok) {
           // thresholds published by other units of this row; the load was issued one tile ago
           if (next_hint != 0u) thr = fmaxf(thr, key_to_float(next_hint));
           next_hint = __ldcg(&P.thr_hint[grow]);
         }
+        if (t == t0) unit_cold = __ballot_sync(0xffffffffu, row_ok && thr == -INFINITY) != 0u;
         ptx::mbar_wait(ptx::smem_u32(&s_tmem_full[acc]), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
@@ -584,7 +617,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
+            if (CTAS == 2) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
             else ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
           }
           acc ^= 1u;
@@ -596,10 +629,14 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // that pass 2 -- the normal filter below -- appends those instead of most of the tile, and
         // the next tiles start from a "20th best of 256" threshold.  Without it a cold unit
         // spends its first three tiles appending and compacting (profiles/small_q_trace.py).
-        bool update_cm = true;
+        // chunkmax == 2: the running top-20 of chunk maxima is only kept by units that started cold
+        // (some row without a threshold); a warm unit filters against thresholds other units have
+        // published, which the chunk maxima would not raise before the buffer's own compaction does,
+        // and the 40-instruction sorted insertion on every chunk with a hit is the largest single item
+        // of the epilogue's slow path
+        bool update_cm = P.chunkmax != 2 || unit_cold;
         if (tracing && t == t0) g_trace_ns[blockIdx.x * kTraceTiles + 40] = globaltimer_ns();
-        if (!DENSE && P.chunkmax && t == t0 &&
-            __ballot_sync(0xffffffffu, row_ok && thr == -INFINITY) != 0u) {
+        if (!DENSE && P.chunkmax && t == t0 && unit_cold) {
           uint32_t vc[32];
 #pragma unroll 1
           for (int chunk = 0; chunk < BN / 32; ++chunk) {
@@ -642,7 +679,7 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
+              if (CTAS == 2) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
               else ptx::mbar_arrive(ptx::smem_u32(&s_tmem_empty[acc]));
             }
           }
@@ -682,6 +719,337 @@ score_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     ptx::tc_fence_after();
     if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ==========================================================================================
+// Query-stationary variant (CTA pairs, D_pad <= 768): the pair's 256-query block is loaded ONCE per
+// work unit and stays on chip for the whole stripe; only corpus rows stream through the smem ring.
+// Against the kernel above this halves the operand traffic L2 -> SM per FLOP (768 KB -> 384 KB per
+// 256 x 256 block of scores at D = 768) and the shared-memory port load (no query tile is written
+// and re-read per corpus tile), and the producer issues ONE 32 KB box per 1024 cycles of MMA work.
+//
+// Where the query block lives (per CTA: 128 rows x D_pad bf16 = up to 192 KB):
+//   k-blocks [0, 8)      TENSOR MEMORY, columns [0, 256): lane r = query row r, column c = bf16
+//                        elements (2c, 2c+1); the MMAs read it as their A operand from TMEM
+//   k-blocks [8, 12)     shared memory, 128B-swizzled K-major like a TMA-staged tile (64 KB), read
+//                        through a descriptor; loaded by one TMA box per unit
+// TMEM columns [256, 512): two fp32 accumulators of ACC_N = 128 corpus rows, double-buffered (N = 128
+// is the smallest N that runs at the full MMA rate: 64.0 cycles per instruction, N = 64 takes 44.6
+// instead of 32 -- profiles/ubench_umma.cu).  A plan tile (256 corpus rows) is walked as two
+// sub-tiles; a sub-tile's MMAs run over all k-blocks before the next one starts.
+// smem ring: 4 stages of QS_KB_STAGE = 4 k-blocks of ONE CTA's half of a sub-tile (64 rows): one 3-D
+// TMA box {64 k, 64 rows, 4 k-blocks} = 32 KB per stage.
+// ==========================================================================================
+constexpr int QS_KB_STAGE = 4;
+constexpr int QS_MAX_DPAD = 768;
+constexpr int QS_KB_TMEM = 8;                                   // k-blocks of the query block kept in TMEM
+constexpr int QS_ACC_N = 128;
+constexpr int QS_STAGES = 4;
+constexpr int QS_B_ROWS = QS_ACC_N / 2;                          // corpus rows one CTA stages per sub-tile
+constexpr uint32_t QS_KB_BYTES = QS_B_ROWS * BK * 2;             // 8 KB: one k-block of that half
+constexpr uint32_t QS_STAGE_BYTES = QS_KB_BYTES * QS_KB_STAGE;   // 32 KB
+constexpr uint32_t QS_ATAIL_BYTES = (QS_MAX_DPAD / BK - QS_KB_TMEM) * A_BYTES;   // 64 KB
+constexpr size_t QS_SMEM = (size_t)QS_ATAIL_BYTES + (size_t)QS_STAGES * QS_STAGE_BYTES + 1024;
+constexpr uint32_t QS_ACC_BASE = TMEM_COLS - 2 * QS_ACC_N;
+constexpr int QS_SUB = BN / QS_ACC_N;                            // sub-tiles per plan tile
+
+// This thread's query row (or zeros) -> its TMEM lane, 32 columns (= 64 bf16 = 8 x 16 bytes) per store.
+__device__ __forceinline__ void qs_load_query_row(const uint4* __restrict__ qrow, bool ok, uint32_t taddr, int a_cols) {
+#pragma unroll 2
+  for (int c0 = 0; c0 < a_cols; c0 += 32) {
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 x = ok ? __ldg(qrow + (c0 >> 2) + j) : make_uint4(0u, 0u, 0u, 0u);
+      v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+    ptx::tmem_st_32x32(taddr + (uint32_t)c0, v);
+  }
+  ptx::tmem_st_wait();
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_select_qs_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q,
+                       const ScoreParams P) {
+  constexpr int ACC_N = QS_ACC_N;
+  constexpr int NCHUNK = ACC_N / 32;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[QS_STAGES];
+  __shared__ __align__(8) uint64_t s_empty[QS_STAGES];
+  __shared__ __align__(8) uint64_t s_tmem_full[2];
+  __shared__ __align__(8) uint64_t s_tmem_empty[2];
+  __shared__ __align__(8) uint64_t s_a_ready;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_hist[4][256];
+  __shared__ float s_stage[4][32 * kStagePitch];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kWarpTma = 4, kWarpMma = 5, kWarpAlloc = 6;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int group = blockIdx.x / 2, n_groups = gridDim.x / 2;
+  const uint32_t smem_atail = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // query k-blocks >= QS_KB_TMEM
+  const uint32_t smem_ring = smem_atail + QS_ATAIL_BYTES;
+  const int stages_per_sub = (P.num_kb + QS_KB_STAGE - 1) / QS_KB_STAGE;
+  const int n_sub = (P.N + ACC_N - 1) / ACC_N;
+  const int kb_tmem = min(P.num_kb, QS_KB_TMEM);
+  const int kb_tail = P.num_kb - kb_tmem;        // 0..4 k-blocks of the query block in shared memory
+
+  if (warp == kWarpTma && lane == 0) { ptx::prefetch_tmap(&tmap_c); ptx::prefetch_tmap(&tmap_q); }
+  if (warp == kWarpMma && lane == 0) {
+    for (int s = 0; s < QS_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&s_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(ptx::smem_u32(&s_tmem_full[a]), 1);
+      ptx::mbar_init(ptx::smem_u32(&s_tmem_empty[a]), 8);   // 4 epilogue warps of each CTA
+    }
+    // query block in place: one arrival per epilogue warp of both CTAs (the leader's warp 0 arrives
+    // with the byte count of both CTAs' smem parts)
+    ptx::mbar_init(ptx::smem_u32(&s_a_ready), 8);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kWarpAlloc) ptx::tmem_alloc_pair(ptx::smem_u32(&s_tmem_base), TMEM_COLS);
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == kWarpTma) {
+    // ============================== TMA producer (corpus rows only; whole warp, one lane issues) ===
+    uint32_t stage = 0, phase = 0;
+    for (int u = group; u < P.units; u += n_groups) {
+      const int s = u / P.m_tiles;
+      const int sub0 = s * P.tiles_per_stripe * QS_SUB;
+      const int sub1 = min(min(s * P.tiles_per_stripe + P.tiles_per_stripe, P.n_tiles) * QS_SUB, n_sub);
+      for (int sub = sub0; sub < sub1; ++sub) {
+        const int c_row = (P.debug & 4) ? 0 : sub * ACC_N + (int)rank * QS_B_ROWS;
+        for (int st = 0; st < stages_per_sub; ++st) {
+          ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
+          if (ptx::elect_one_sync()) {
+            const uint32_t full = ptx::smem_u32(&s_full[stage]);
+            // k-blocks past the end of the row (last stage of a sub-tile when num_kb % 4 != 0) are
+            // zero-filled by TMA and still counted: the byte count of a stage is always the whole box
+            if (rank == 0) ptx::mbar_arrive_expect_tx(full, QS_STAGE_BYTES * 2u);
+            ptx::tma_load_3d_pair(smem_ring + stage * QS_STAGE_BYTES, &tmap_c, ptx::mapa_shared(full, 0), 0, c_row,
+                                  st * QS_KB_STAGE, ptx::kEvictNormal);
+          }
+          __syncwarp();
+          if (++stage == QS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kWarpMma && rank == 0) {
+    // ============================== MMA issuer (whole warp, one lane issues) ================================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM * 2, ACC_N);
+    const uint64_t da_tail = ptx::make_sw128_kmajor_desc(smem_atail);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
+    for (int u = group; u < P.units; u += n_groups) {
+      const int s = u / P.m_tiles;
+      const int sub0 = s * P.tiles_per_stripe * QS_SUB;
+      const int sub1 = min(min(s * P.tiles_per_stripe + P.tiles_per_stripe, P.n_tiles) * QS_SUB, n_sub);
+      // the unit's query block is in TMEM / shared memory of both CTAs
+      ptx::mbar_wait(ptx::smem_u32(&s_a_ready), a_phase);
+      a_phase ^= 1u;
+      ptx::tc_fence_after();
+      for (int sub = sub0; sub < sub1; ++sub) {
+        ptx::mbar_wait(ptx::smem_u32(&s_tmem_empty[acc]), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_u + QS_ACC_BASE + acc * ACC_N;
+        for (int st = 0; st < stages_per_sub; ++st) {
+          const int nkb = min(QS_KB_STAGE, P.num_kb - st * QS_KB_STAGE);
+          ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one_sync()) {
+            const uint64_t db = ptx::make_sw128_kmajor_desc(smem_ring + stage * QS_STAGE_BYTES);
+            // a stage lies entirely on one side of the TMEM / smem split of the query block
+            // (QS_KB_TMEM is a multiple of QS_KB_STAGE): ONE decision per 16 MMAs, and every operand
+            // of the unrolled MMAs is a base plus a compile-time offset
+            if (st * QS_KB_STAGE < QS_KB_TMEM) {
+              const uint32_t a0 = tmem_u + (uint32_t)(st * QS_KB_STAGE * (BK / 2));
+#pragma unroll
+              for (int kbi = 0; kbi < QS_KB_STAGE; ++kbi) {
+                if (kbi < nkb) {
+#pragma unroll
+                  for (int k = 0; k < BK / UMMA_K; ++k)   // A: 16 bf16 = 8 TMEM columns per K step
+                    ptx::umma_bf16_pair_ts(d_tmem, a0 + (uint32_t)(kbi * (BK / 2) + k * (UMMA_K / 2)),
+                                           db + (uint64_t)(kbi * (QS_KB_BYTES >> 4) + 2 * k), idesc,
+                                           (kbi | k) != 0 ? 1u : (st != 0 ? 1u : 0u));
+                }
+              }
+            } else {
+              const uint64_t a0 = da_tail + (uint64_t)((st * QS_KB_STAGE - QS_KB_TMEM) * (A_BYTES >> 4));
+#pragma unroll
+              for (int kbi = 0; kbi < QS_KB_STAGE; ++kbi) {
+                if (kbi < nkb) {
+#pragma unroll
+                  for (int k = 0; k < BK / UMMA_K; ++k)   // A: one 16 KB swizzled tile per k-block, +32 bytes per K step
+                    ptx::umma_bf16_pair(d_tmem, a0 + (uint64_t)(kbi * (A_BYTES >> 4) + 2 * k),
+                                        db + (uint64_t)(kbi * (QS_KB_BYTES >> 4) + 2 * k), idesc, 1u);
+                }
+              }
+            }
+            ptx::umma_commit_pair(ptx::smem_u32(&s_empty[stage]), 3);
+            if (st + 1 == stages_per_sub) ptx::umma_commit_pair(ptx::smem_u32(&s_tmem_full[acc]), 3);
+          }
+          __syncwarp();
+          if (++stage == QS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp < 4) {
+    // ============================== epilogue ==================================
+    const int quarter = warp;
+    const int row_in_unit = (int)rank * BM + quarter * 32 + lane;
+    int* hist = s_hist[quarter];
+    float* stage = s_stage[quarter];
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t a_ready_leader = ptx::mapa_shared(ptx::smem_u32(&s_a_ready), 0);
+    const int a_cols = kb_tmem * (BK / 2);
+    // Puts the query block of unit `un` in place (this thread: its own row -> TMEM; warp 0 lane 0:
+    // the TMA box of the k-blocks that live in shared memory) and arrives on the leader's barrier.
+    auto stage_queries = [&](int un) {
+      const int gn = (un % P.m_tiles) * (2 * BM) + row_in_unit;
+      if (P.debug & 128) {   // ablation: no staging work, only the handshake
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster_relaxed(a_ready_leader);
+        return;
+      }
+      if (quarter == 0 && lane == 0 && kb_tail > 0) {
+        // both CTAs' boxes are accounted on the leader's barrier; rows past Q are zero-filled
+        ptx::tma_load_3d_pair(smem_atail, &tmap_q, a_ready_leader, 0, (un % P.m_tiles) * (2 * BM) + (int)rank * BM, QS_KB_TMEM,
+                              ptx::kEvictLast);
+      }
+      qs_load_query_row(P.q_rows + (size_t)gn * P.q_pitch16, gn < P.Q, lane_base, a_cols);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (quarter == 0 && rank == 0 && kb_tail > 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&s_a_ready), 2u * QS_ATAIL_BYTES);
+        else ptx::mbar_arrive_cluster_relaxed(a_ready_leader);
+      }
+    };
+    uint32_t acc = 0, acc_phase = 0;
+    bool a_stored = false;
+    for (int u = group; u < P.units; u += n_groups) {
+      const int s = u / P.m_tiles, m = u - s * P.m_tiles;
+      const int sub0 = s * P.tiles_per_stripe * QS_SUB;
+      const int sub1 = min(min(s * P.tiles_per_stripe + P.tiles_per_stripe, P.n_tiles) * QS_SUB, n_sub);
+      const int grow = m * (2 * BM) + row_in_unit;
+      if (!a_stored) {   // first unit of this CTA (later ones are staged at the end of the previous unit)
+        stage_queries(u);
+        a_stored = true;
+      }
+      const bool row_ok = grow < P.Q && !(P.debug & 16);
+      float thr = row_ok ? -INFINITY : INFINITY;
+      float pub = thr;
+      float cm[kChunkMax];
+#pragma unroll
+      for (int i = 0; i < kChunkMax; ++i) cm[i] = -INFINITY;
+      int cnt = 0;
+      uint2* my_buf = DENSE ? nullptr : P.unit_cand + ((size_t)u * (2 * BM) + row_in_unit) * (size_t)P.cap;
+      uint32_t next_hint = (!DENSE && row_ok) ? __ldcg(&P.thr_hint[grow]) : 0u;
+      bool unit_cold = false;
+      for (int sub = sub0; sub < sub1; ++sub) {
+        const bool tile_start = ((sub - sub0) % QS_SUB) == 0;
+        if (!DENSE && row_ok && tile_start) {
+          if (next_hint != 0u) thr = fmaxf(thr, key_to_float(next_hint));
+          next_hint = __ldcg(&P.thr_hint[grow]);
+        }
+        if (sub == sub0) unit_cold = __ballot_sync(0xffffffffu, row_ok && thr == -INFINITY) != 0u;
+        ptx::mbar_wait(ptx::smem_u32(&s_tmem_full[acc]), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = lane_base + QS_ACC_BASE + acc * ACC_N;
+        const bool last_of_unit = sub + 1 == sub1;
+        if (P.debug & 1) {  // ablation: no TMEM reads at all
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
+        } else {
+          // Cold start (first sub-tile of a unit whose rows have no threshold yet): pass 1 collects
+          // each chunk's four best scores into the running top-20, pass 2 is the normal filter against
+          // the resulting threshold, so the unit appends ~20 entries per row instead of the sub-tile.
+          bool update_cm = P.chunkmax != 2 || unit_cold;   // see the classic kernel
+          if (!DENSE && P.chunkmax && sub == sub0 && unit_cold) {
+            uint32_t vc[32];
+#pragma unroll 1
+            for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+              ptx::tmem_ld_32x32(taddr + chunk * 32, vc);
+              ptx::tmem_ld_wait(vc);
+              const int col0 = sub * ACC_N + chunk * 32;
+              // eight best of the chunk (sorted insertion), then those into cm[]: 20 of the 32
+              // documents collected over the sub-tile score >= cm[19]
+              float c8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) c8[i] = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = (col0 + j < P.N) ? __uint_as_float(vc[j]) : -INFINITY;
+#pragma unroll
+                for (int i = 7; i > 0; --i) c8[i] = fmaxf(c8[i], fminf(c8[i - 1], x));
+                c8[0] = fmaxf(c8[0], x);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) cm_insert(cm, c8[i]);
+            }
+            if (row_ok) thr = fmaxf(thr, cm[kChunkMax - 1]);
+            update_cm = false;
+          }
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_32x32(taddr, va);
+          ptx::tmem_ld_wait(va);
+#pragma unroll 1
+          for (int chunk = 0; chunk < NCHUNK; chunk += 2) {
+            ptx::tmem_ld_32x32(taddr + (chunk + 1) * 32, vb);
+            epilogue_chunk<DENSE>(va, sub * ACC_N + chunk * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane, cm,
+                                  update_cm);
+            ptx::tmem_ld_wait(vb);
+            if (chunk + 2 < NCHUNK) {
+              ptx::tmem_ld_32x32(taddr + (chunk + 2) * 32, va);
+            } else {
+              // every column of this accumulator is in registers: hand it back to the MMA warp
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_shared(ptx::smem_u32(&s_tmem_empty[acc]), 0));
+            }
+            epilogue_chunk<DENSE>(vb, sub * ACC_N + (chunk + 1) * 32, P, grow, row_ok, thr, cnt, my_buf, stage, hist, lane,
+                                  cm, update_cm);
+            if (chunk + 2 < NCHUNK) ptx::tmem_ld_wait(va);
+          }
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+        if (!DENSE && row_ok && thr > pub && (((sub + 1 - sub0) % QS_SUB) == 0 || last_of_unit)) {
+          publish_threshold(P, grow, float_to_key(thr));
+          pub = thr;
+        }
+      }
+      // Every accumulator of this unit has been read, so all of its MMAs have completed and the query
+      // block (TMEM and smem part) is free: stage the NEXT unit's block first -- the tensor pipe
+      // restarts while this unit's buffers are being compacted below.
+      if (u + n_groups < P.units) stage_queries(u + n_groups);
+      if (!DENSE) {
+        unsigned need = __ballot_sync(0xffffffffu, cnt > P.kunit);
+        if (P.cap <= kSmallCap && P.chunkmax) need = final_filter_rows(need, P.kunit + 16, thr, cnt, my_buf, lane);
+        compact_rows(need, P.cap, P, grow, thr, cnt, my_buf, hist, lane);
+        P.unit_cnt[(size_t)u * (2 * BM) + row_in_unit] = cnt;
+        P.unit_thr[(size_t)u * (2 * BM) + row_in_unit] = row_ok ? float_to_key(thr) : 0u;
+      }
+    }
+  }
+
+  // ------------------------------ teardown ------------------------------
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == kWarpAlloc) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -746,6 +1114,69 @@ static int launch_score_t(const void* q_bf16, const void* c_bf16, const ScorePar
   cfg.numAttrs = 1;
   QST_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tc, P));
   return QST_OK;
+}
+
+// bf16 [rows, d_pad] row-major seen as {64 k, rows, d_pad/64 k-blocks}: one box = box_rows rows x
+// box_kb k-blocks, written to smem as box_kb consecutive 128B-swizzled [box_rows x 64] tiles.  Rows and
+// k-blocks out of range are zero-filled.
+static int make_tmap_3d(CUtensorMap* map, const void* base, int64_t rows, int64_t d_pad, int box_rows, int box_kb) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return QST_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)(d_pad / BK)};
+  cuuint64_t gstride[2] = {(cuuint64_t)d_pad * 2, (cuuint64_t)BK * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_kb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r); return QST_ERR_CUDA; }
+  return QST_OK;
+}
+
+template <bool DENSE>
+static int launch_score_qs_t(const void* q_bf16, const void* c_bf16, ScoreParams P, int64_t d_pad, int groups,
+                             cudaStream_t st) {
+  CUtensorMap tc, tq;
+  int rc = make_tmap_3d(&tc, c_bf16, P.N, d_pad, QS_B_ROWS, QS_KB_STAGE);
+  if (rc) return rc;
+  // query k-blocks [QS_KB_TMEM, 12) of one CTA's 128 rows in one box
+  rc = make_tmap_3d(&tq, q_bf16, P.Q, d_pad, BM, QS_MAX_DPAD / BK - QS_KB_TMEM);
+  if (rc) return rc;
+  P.q_rows = reinterpret_cast<const uint4*>(q_bf16);
+  P.q_pitch16 = (int)(d_pad / 8);
+  auto kern = score_select_qs_kernel<DENSE>;
+  QST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QS_SMEM));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(groups * 2));
+  cfg.blockDim = dim3(kScoreThreads);
+  cfg.dynamicSmemBytes = QS_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  QST_CUDA(cudaLaunchKernelEx(&cfg, kern, tc, tq, P));
+  return QST_OK;
+}
+
+static int launch_score_qs(bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P_in, int64_t d_pad,
+                           int groups, cudaStream_t st) {
+  ScoreParams P = P_in;
+  const char* dbg = getenv("QST_SCORE_DEBUG");
+  P.debug = dbg ? atoi(dbg) : 0;
+  return dense ? launch_score_qs_t<true>(q_bf16, c_bf16, P, d_pad, groups, st)
+               : launch_score_qs_t<false>(q_bf16, c_bf16, P, d_pad, groups, st);
+}
+
+// Query-stationary tiles for CTA pairs whenever the query block fits TMEM next to two accumulators;
+// QST_SCORE_QS=0 forces the classic (query tiles re-staged per corpus tile) pair kernel.
+static bool use_query_stationary(int ctas, int64_t d_pad) {
+  const char* e = getenv("QST_SCORE_QS");
+  if (e && e[0] == '0') return false;
+  return ctas == 2 && d_pad <= QS_MAX_DPAD;
 }
 
 static int launch_score(int ctas, bool dense, const void* q_bf16, const void* c_bf16, const ScoreParams& P_in,
@@ -827,6 +1258,7 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
   plan->k = k; plan->kprime = kprime;
   plan->score = score;
   plan->ctas = default_ctas(Q);
+  plan->qs = use_query_stationary(plan->ctas, plan->D_pad) ? 1 : 0;
   plan->rows_per_unit = BM * plan->ctas;
   plan->m_tiles = (int)ceil_div(Q, plan->rows_per_unit);
   plan->n_tiles = (int)ceil_div(N, BN);
@@ -926,8 +1358,8 @@ static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, cons
   P.kunit = plan->kunit; P.cap = plan->cap;
   // the count-20 chunk-maximum thresholds are as safe as the buffer's own when a unit is expected to
   // hold at most ~5 of the k' best documents (kunit = 3*lambda + 8 <= 24)
-  P.chunkmax = plan->kunit <= 24 ? 1 : 0;
-  { const char* e = getenv("QST_CHUNKMAX"); if (e) P.chunkmax = atoi(e) != 0; }
+  P.chunkmax = plan->kunit <= 24 ? 2 : 0;   // 2 = cold units only, 1 = every unit (QST_CHUNKMAX overrides)
+  { const char* e = getenv("QST_CHUNKMAX"); if (e) P.chunkmax = atoi(e); }
   // hint array: inside the workspace (zeroed here) or, for sharded runs, the caller's peer-visible
   // buffer, which the CALLER zeroes (it is written by other ranks, see qst_peer_buffer_*)
   P.thr_hint = hint_local ? hint_local : reinterpret_cast<uint32_t*>(ws + plan->off_thr);
@@ -939,6 +1371,11 @@ static int score_select_impl(const qst_topk_plan* plan, const void* q_bf16, cons
   QST_CHECK_ARG(plan->ctas == 1 || plan->ctas == 2, "score_select: plan->ctas must be 1 or 2");
   if (!hint_local)
     QST_CUDA(cudaMemsetAsync(P.thr_hint, 0, (size_t)plan->m_tiles * plan->rows_per_unit * sizeof(uint32_t), st));
+  if (plan->qs) {
+    QST_CHECK_ARG(plan->ctas == 2 && plan->D_pad <= QS_MAX_DPAD, "score_select: plan->qs needs CTA pairs and D_pad <= %d",
+                  QS_MAX_DPAD);
+    return launch_score_qs(false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
+  }
   return launch_score(plan->ctas, false, q_bf16, c_bf16, P, plan->D_pad, plan->grid, st);
 }
 
@@ -964,5 +1401,7 @@ extern "C" int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16
   if (sms <= 0) sms = 148;
   const int groups_max = sms / ctas;
   const int groups = P.units < groups_max ? P.units : groups_max;
+  if (use_query_stationary(ctas, D_pad))
+    return launch_score_qs(true, q_bf16, c_bf16, P, D_pad, groups, reinterpret_cast<cudaStream_t>(stream));
   return launch_score(ctas, true, q_bf16, c_bf16, P, D_pad, groups, reinterpret_cast<cudaStream_t>(stream));
 }

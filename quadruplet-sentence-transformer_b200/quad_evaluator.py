@@ -41,6 +41,27 @@ class SimilarityFunction(Enum):
 _PAIRS = ("pos_part", "pos_neg", "part_neg")
 
 
+def normalize_similarity_function(f):
+    """``main_distance_function`` as the local enum.  The reference call sites pass
+    ``sentence_transformers.evaluation.SimilarityFunction`` members (``models/evaluators.py:10, 148``):
+    a foreign enum never compares equal to ours, so members are matched by ``.name`` (then ``.value``),
+    plain strings / ints are accepted too, and anything unknown raises instead of silently falling
+    through to "best of the three"."""
+    if f is None or isinstance(f, SimilarityFunction):
+        return f
+    name = getattr(f, "name", f if isinstance(f, str) else None)
+    if isinstance(name, str) and name.upper() in SimilarityFunction.__members__:
+        return SimilarityFunction[name.upper()]
+    value = getattr(f, "value", f)
+    if isinstance(value, int) and not isinstance(value, bool):
+        try:
+            return SimilarityFunction(value)
+        except ValueError:
+            pass
+    raise ValueError(f"main_distance_function must be None or a SimilarityFunction (COSINE, EUCLIDEAN, MANHATTAN, "
+                     f"DOT_PRODUCT), {f!r} given")
+
+
 def paired_distance_counts(anchor: torch.Tensor, pos: torch.Tensor, part: torch.Tensor, neg: torch.Tensor,
                            want_distances: bool = False):
     """``qst_quadruplet_eval``: counts [3 metrics (cos, manhattan, euclid), 3 pairs] as a CPU int64
@@ -94,7 +115,7 @@ class QuadrupletEvaluator:
         self.name = name
         self._gamma = gamma
         self._all_examples = all_examples
-        self.main_distance_function = main_distance_function
+        self.main_distance_function = normalize_similarity_function(main_distance_function)
         self.batch_size = batch_size
         self.show_progress_bar = bool(show_progress_bar)
         self.write_csv = write_csv
@@ -131,7 +152,7 @@ class QuadrupletEvaluator:
 
     def _pick(self, acc_cos: float, acc_manhattan: float, acc_euclid: float) -> float:
         """Return value of one TripletEvaluator call (ST 2.2.2)."""
-        f = self.main_distance_function
+        f = normalize_similarity_function(self.main_distance_function)   # the attribute may be re-assigned
         if f == SimilarityFunction.COSINE:
             return acc_cos
         if f == SimilarityFunction.MANHATTAN:

@@ -60,6 +60,8 @@ def test_plan_invariants(lib):
                 plan = qst_b200._lib.TopkPlan()
                 assert lib.qst_topk_plan_make(Q, N, D, k, 0, 0, 148, C.byref(plan)) == 0
                 assert plan.ctas == int(ctas) and plan.rows_per_unit == 128 * plan.ctas
+                # query-stationary tiles: CTA pairs whose query block fits TMEM + 64 KB of smem
+                assert plan.qs == (1 if plan.ctas == 2 and plan.D_pad <= 768 else 0)
                 assert plan.D_pad % 64 == 0 and plan.D_pad >= D
                 assert plan.kprime >= k and plan.kprime % 16 == 0
                 assert min(16, plan.kprime) <= plan.kunit <= plan.kprime and plan.cap >= plan.kunit + 64
@@ -104,7 +106,8 @@ def test_struct_layouts():
     import qst_b200
     assert C.sizeof(qst_b200._lib.QuadParams) == 32
     assert qst_b200._lib.TopkPlan.ws_bytes.offset % 8 == 0
-    assert C.sizeof(qst_b200._lib.TopkPlan) == 32 + 4 * 14 + 8 * 5
+    assert C.sizeof(qst_b200._lib.TopkPlan) == 32 + 4 * 14 + 8 * 5 + 8     # + qs flag and padding
+    assert qst_b200._lib.TopkPlan.qs.offset == 32 + 4 * 14 + 8 * 5
 
 
 def test_product_refuses_cpu_tensors_and_has_no_oracle_dependency():

@@ -14,11 +14,14 @@ def _dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+@pytest.fixture(params=[(2, 1), (2, 0), (1, 0)], ids=["cta_pair_qs", "cta_pair", "single_cta"])
 def ctas(request, monkeypatch):
-    """Both tile shapes of K2: cta_group::2 pairs (default) and the single-CTA tile."""
-    monkeypatch.setenv("QST_SCORE_CTAS", str(request.param))
-    return request.param
+    """The three K2 kernels: cta_group::2 pairs with the query block resident in TMEM (default for
+    D_pad <= 768), pairs that re-stage the query tile per corpus tile, and the single-CTA tile."""
+    n, qs = request.param
+    monkeypatch.setenv("QST_SCORE_CTAS", str(n))
+    monkeypatch.setenv("QST_SCORE_QS", str(qs))
+    return n
 
 
 def _fp64_scores(q, c, idx, score):

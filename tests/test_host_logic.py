@@ -146,6 +146,24 @@ def test_ir_evaluation_set_loader_and_quadruplet_evaluator_construction(tmp_path
     qe.main_distance_function = qst_b200.SimilarityFunction.EUCLIDEAN
     assert qe._pick(0.1, 0.3, 0.2) == 0.2
     assert [m.value for m in qst_b200.SimilarityFunction] == [0, 1, 2, 3]
+    # the reference passes sentence_transformers.evaluation.SimilarityFunction members
+    # (models/evaluators.py:10, 148): a foreign enum with the same names must select the same accuracy
+    import enum
+
+    class ForeignSimilarityFunction(enum.Enum):
+        COSINE = 0
+        EUCLIDEAN = 1
+        MANHATTAN = 2
+        DOT_PRODUCT = 3
+
+    for member, want in ((ForeignSimilarityFunction.COSINE, 0.1), (ForeignSimilarityFunction.MANHATTAN, 0.3),
+                         (ForeignSimilarityFunction.EUCLIDEAN, 0.2), (ForeignSimilarityFunction.DOT_PRODUCT, 0.3)):
+        q2 = qst_b200.QuadrupletEvaluator(["a"], ["b"], ["c"], ["d"], main_distance_function=member)
+        assert q2._pick(0.1, 0.3, 0.2) == want
+        qe.main_distance_function = member          # re-assigned attribute, as a caller may do
+        assert qe._pick(0.1, 0.3, 0.2) == want
+    with pytest.raises(ValueError):
+        qst_b200.QuadrupletEvaluator(["a"], ["b"], ["c"], ["d"], main_distance_function="chebyshev")
     with pytest.raises(AssertionError):
         qst_b200.QuadrupletEvaluator(["a"], ["b", "x"], ["c"], ["d"])
 
