@@ -45,6 +45,9 @@ enum qst_status {
 
 int qst_version(void);
 const char* qst_last_error(void);
+/* Number of kernels this library has launched so far in this process (all entry points, all
+ * threads): the difference around a region is the number of OUR kernels that ran in it. */
+long long qst_launch_count(void);
 /* SM count / compute capability of the current device. */
 int qst_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

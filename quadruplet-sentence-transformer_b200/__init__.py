@@ -30,7 +30,7 @@ from .scoring import (CorpusIndex, HostTopkPipeline, TopkResult, cos_sim, dot_sc
 from .ir_evaluator import InformationRetrievalEvaluator, load_ir_evaluation_set
 from .quad_evaluator import QuadrupletEvaluator, SimilarityFunction, paired_distance_counts
 from .loss_evaluator import QuadrupletLossEvaluator, dissimilar_mask, incremental_mean_f32
-from . import metrics, synth
+from . import comm, metrics, synth
 from .sharded import ShardedCorpus
 
 __all__ = [
@@ -38,5 +38,5 @@ __all__ = [
     "InformationRetrievalEvaluator", "cos_sim", "dot_score", "euclidean_score", "CorpusIndex", "TopkResult", "topk",
     "topk_host", "HostTopkPipeline", "prepare_rows", "QuadrupletEvaluator", "SimilarityFunction", "paired_distance_counts",
     "QuadrupletLossEvaluator", "dissimilar_mask", "incremental_mean_f32",
-    "load_ir_evaluation_set", "ShardedCorpus", "metrics", "synth", "QstError", "QstLibraryError",
+    "load_ir_evaluation_set", "ShardedCorpus", "comm", "metrics", "synth", "QstError", "QstLibraryError",
 ]

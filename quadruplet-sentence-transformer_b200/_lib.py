@@ -54,6 +54,7 @@ _INT = C.c_int
 SIGNATURES = {
     "qst_version": (_INT, []),
     "qst_last_error": (C.c_char_p, []),
+    "qst_launch_count": (C.c_longlong, []),
     "qst_device_info": (_INT, [C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)]),
     "qst_quadruplet_workspace_bytes": (C.c_size_t, []),
     "qst_quadruplet_fwd": (_INT, [_P, _P, _P, _P, _INT, _I64, _I64, C.POINTER(QuadParams), _INT, _P, _P, _P, _P]),

@@ -1,0 +1,227 @@
+"""Collectives of the corpus-sharded path behind one small interface.
+
+The sharded retrieval needs four things from "the other ranks": an all-gather, an all-to-all (equal
+blocks), a MAX all-reduce of a few floats, and device buffers every rank of the node can write
+(threshold hints pushed with remote atomics while K2 runs).  Three implementations:
+
+* ``TorchComm``  -- ``torch.distributed`` (backend ``nccl`` on GPUs over NVLink/NVSwitch, ``gloo`` in the
+  CPU tests of the plumbing); peer-writable buffers through CUDA IPC.
+* ``NcclComm``   -- NCCL called directly through the C ABI (``qst_comm_*`` in ``include/qst.h``), no
+  ``torch.distributed`` on the data path; the unique id is exchanged by the caller.
+* ``LocalComm``  -- G ranks as G THREADS of one process on one GPU.  Exists so that the sharded code path
+  (not a re-statement of it) runs in the single-GPU test tier: collectives are tensor copies behind a
+  ``threading.Barrier``, "peer" buffers are plain allocations every thread can address.
+
+All tensor collectives are stream-ordered on the caller's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+class SharedBuffers:
+    """One zero-filled device buffer per rank, writable by every rank: ``local`` is this rank's own,
+    ``peers`` the other ranks' (mapped) pointers in rank order."""
+
+    def __init__(self, local: int, peers: Sequence[int], closer=None, keep=None):
+        self.local, self.peers, self._closer, self._keep = int(local), [int(p) for p in peers], closer, keep
+
+    def close(self):
+        if self._closer is not None:
+            self._closer()
+            self._closer = None
+        self._keep = None
+
+
+class Comm:
+    world: int
+    rank: int
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """[n, ...] per rank -> [world * n, ...] (rank-major) on every rank."""
+        raise NotImplementedError
+
+    def all_to_all(self, t: torch.Tensor) -> torch.Tensor:
+        """[world * n, ...] (block r goes to rank r) -> [world * n, ...] (block r came from rank r)."""
+        raise NotImplementedError
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def barrier(self) -> None:
+        raise NotImplementedError
+
+    def shared_buffers(self, nbytes: int, device: torch.device) -> Optional[SharedBuffers]:
+        """Collective.  None when peer-writable memory is not available (the caller then does without)."""
+        return None
+
+
+class SingleComm(Comm):
+    """World of one: every collective is the identity."""
+    world, rank = 1, 0
+
+    def all_gather(self, t):
+        return t
+
+    def all_to_all(self, t):
+        return t
+
+    def all_reduce_max(self, t):
+        return t
+
+    def barrier(self):
+        pass
+
+
+class TorchComm(Comm):
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def all_gather(self, t):
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self._dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    def all_to_all(self, t):
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        self._dist.all_to_all_single(out, t, group=self.group)
+        return out
+
+    def all_reduce_max(self, t):
+        t = t.clone()
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def barrier(self):
+        self._dist.barrier(self.group)
+
+    def shared_buffers(self, nbytes, device):
+        """cudaMalloc + CUDA IPC handles exchanged with an all-gather; all ranks or none."""
+        if torch.device(device).type != "cuda":
+            return None
+        lib = _lib.load()
+        dist = self._dist
+        local, peers, ok = C.c_void_p(), [], 1
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            if lib.qst_peer_buffer_create(nbytes, C.byref(local), handle) != 0:
+                ok, local = 0, C.c_void_p()
+            mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+            every = self.all_gather(mine).cpu().view(self.world, 64)
+            if ok:
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    p = C.c_void_p()
+                    if lib.qst_peer_buffer_open(bytes(every[r].tolist()), C.byref(p)) != 0:
+                        ok = 0
+                        break
+                    peers.append(p)
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+
+        def closer():
+            for p in peers:
+                lib.qst_peer_buffer_close(p)
+            if local:
+                lib.qst_peer_buffer_destroy(local)
+
+        if not bool(int(flag)):
+            closer()
+            return None
+        return SharedBuffers(local.value, [p.value for p in peers], closer)
+
+
+class _LocalWorld:
+    """State shared by the G ``LocalComm`` threads of one emulated node."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots: List[object] = [None] * world
+        self.failed = threading.Event()
+
+
+class LocalComm(Comm):
+    """Rank of a node emulated by threads of ONE process on ONE device.  Every thread must issue its
+    CUDA work on the same stream (the default stream of the device: work is then totally ordered in
+    submission order, and a host-side barrier between "deposit" and "read" is all a collective needs)."""
+
+    def __init__(self, shared: _LocalWorld, rank: int):
+        self._w, self.world, self.rank = shared, shared.world, rank
+
+    @staticmethod
+    def make_world(world: int) -> List["LocalComm"]:
+        shared = _LocalWorld(world)
+        return [LocalComm(shared, r) for r in range(world)]
+
+    def _exchange(self, obj):
+        w = self._w
+        w.slots[self.rank] = obj
+        w.barrier.wait()
+        got = list(w.slots)
+        w.barrier.wait()          # nobody overwrites a slot before everybody has read it
+        return got
+
+    def all_gather(self, t):
+        return torch.cat([x for x in self._exchange(t.contiguous())])
+
+    def all_to_all(self, t):
+        t = t.contiguous()
+        n = t.shape[0] // self.world
+        got = self._exchange(t)
+        return torch.cat([x[self.rank * n:(self.rank + 1) * n] for x in got])
+
+    def all_reduce_max(self, t):
+        return torch.stack(self._exchange(t)).amax(dim=0)
+
+    def barrier(self):
+        self._w.barrier.wait()
+
+    def shared_buffers(self, nbytes, device):
+        buf = torch.zeros(max(nbytes, 4), dtype=torch.uint8, device=device)
+        ptrs = self._exchange(buf.data_ptr())
+        return SharedBuffers(ptrs[self.rank], [p for r, p in enumerate(ptrs) if r != self.rank], None, keep=buf)
+
+
+def run_local_world(world: int, fn, *args):
+    """Runs ``fn(comm, *args)`` on ``world`` threads (one ``LocalComm`` each); returns the results in
+    rank order, re-raising the first exception of any rank."""
+    comms = LocalComm.make_world(world)
+    out: List[object] = [None] * world
+    err: List[BaseException] = []
+
+    def body(r):
+        try:
+            out[r] = fn(comms[r], *args)
+        except BaseException as e:   # noqa: BLE001 -- re-raised below
+            err.append(e)
+            comms[r]._w.barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if err:
+        real = [e for e in err if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or err)[0]
+    return out
+
+
+def default_comm(group=None) -> Comm:
+    """``TorchComm`` over ``group`` when ``torch.distributed`` is initialised, else a world of one."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return TorchComm(group)
+    return SingleComm()

@@ -25,6 +25,14 @@ extern "C" int qst_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return QST_OK;
 }
 
+// ---- launch counter --------------------------------------------------------------------------------
+#include <atomic>
+namespace qst {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace qst
+extern "C" long long qst_launch_count(void) { return qst::g_launches.load(std::memory_order_relaxed); }
+
 // ---- peer-visible device buffers (CUDA IPC) for the cross-rank threshold hints ------------------
 extern "C" int qst_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle64) {
   QST_CHECK_ARG(dev_ptr && handle64 && bytes > 0, "peer_buffer_create: bad argument");

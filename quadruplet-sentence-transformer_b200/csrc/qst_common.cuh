@@ -31,8 +31,13 @@ void set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+// every kernel launch of the library is counted (qst_launch_count(): bench.py reports how many of
+// OUR kernels ran inside its timed region)
+void count_launch();
+
 #define QST_LAUNCH_CHECK()                                                               \
   do {                                                                                   \
+    ::qst::count_launch();                                                               \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) {                                                            \
       ::qst::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \

@@ -1113,6 +1113,7 @@ static int launch_score_t(const void* q_bf16, const void* c_bf16, const ScorePar
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   QST_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tc, P));
+  count_launch();
   return QST_OK;
 }
 
@@ -1159,6 +1160,7 @@ static int launch_score_qs_t(const void* q_bf16, const void* c_bf16, ScoreParams
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   QST_CUDA(cudaLaunchKernelEx(&cfg, kern, tc, tq, P));
+  count_launch();
   return QST_OK;
 }
 

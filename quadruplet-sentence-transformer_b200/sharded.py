@@ -1,23 +1,30 @@
 """Corpus-sharded retrieval across the GPUs of one node.
 
-One process per GPU (``torch.distributed``, backend ``nccl``; ``gloo`` for the CPU tests of the
-plumbing).  Rank r keeps rows ``shard_bounds(N, G, r)`` of the corpus resident in HBM, every rank
-sees all queries, computes its exact local top-k (global ids = local row + shard offset), the
-per-rank lists are exchanged with ONE all-gather per query tile over NVLink/NVSwitch and merged on
-the device (``qst_merge_topk``: ties -> lower global id).  The all-gather of tile t runs on a side
-stream while tile t+1 is being scored.
+One process per GPU.  Rank r keeps rows ``shard_bounds(N, G, r)`` of the corpus resident in HBM -- the
+bf16 tensor-core operand and, by default, the fp32 master of THOSE ROWS ONLY (the partition of
+BASELINE.json's north star).  The collectives go through a ``qst_b200.comm.Comm``: NCCL over
+NVLink/NVSwitch (``torch.distributed`` or the C ABI's ``qst_comm_*``), ``gloo`` in the CPU tests, or
+threads of one process for the single-GPU test tier.
 
-Two exchange strategies:
+``ShardedCorpus.topk_owned`` (data-parallel entry: every rank brings the queries it owns):
 
-* ``master="sharded"`` (default when no full master is given): every rank rescoring its own k'
-  candidates exactly, one all-gather of the exact per-shard top-k lists, merge (K6).  Works for
-  corpora whose fp32 master does not fit one GPU; rescoring work grows with the number of ranks.
-* ``master="replicated"``: only the bf16 tensor-core operand is sharded; the fp32 master
-  (N*D*4 bytes, 3 GB at 1M x 768) is resident on every rank.  Each shard lists its m best
-  candidates per query by bf16 key (``qst_select_candidates``), ONE all-to-all sends every query's
-  lists to the rank that owns the query, which rescoring-finalises them (``qst_finalize_lists``) and
-  re-scans uncertified ones; an all-gather distributes the final rankings.  Rescoring work per rank
-  stays constant as ranks are added.
+1. all-gather of the fp32 queries, K1 on all G*q of them;
+2. K2 of all queries against the local shard; thresholds are shared between the shards THROUGH PEER
+   MEMORY while the kernels run (``qst_score_select_peers``);
+3. every shard lists its m best candidates per query by bf16 key (``qst_select_candidates``); ONE
+   all-to-all routes each query's G lists to the rank that owns the query;
+4. sharded master: the owner selects the k' best overall and sends every shard the rows it wants
+   rescored (``qst_select_requests`` -> all-to-all), the shard computes their exact fp32 scores from its
+   own rows (``qst_rescore_requests``) -> all-to-all -> ``qst_finalize_exact`` orders them and evaluates
+   the certificate.  Rescoring work per rank is q*k' rows whatever G is; per-GPU memory is the shard only.
+   Replicated master (``full_master=``, 3 GB per 1M x 768 rows on every rank): the owner
+   rescoring-finalises the lists itself (``qst_finalize_lists``), no requests travel;
+5. queries whose certificate failed are re-scanned exactly -- by every shard over its own rows, merged
+   at the owner (sharded master), or by the owner over its copy (replicated master).
+
+``ShardedCorpus.topk(..., strategy="allgather_merge")`` is the literal "local top-k, all-gather, merge":
+every shard finalises its exact local top-k of ALL queries (``qst_finalize_topk``), one all-gather per
+query tile, ``qst_merge_topk`` (ties -> lower global id).  Rescoring work grows with G.
 
 The reference has no multi-GPU path; its only scale-out knob is the sequential corpus chunk loop
 (``corpus_chunk_size``, ``/root/reference/ir_evauation_script.py:161``), which this replaces in
@@ -33,6 +40,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, scoring
+from .comm import Comm, TorchComm, default_comm
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -87,77 +95,57 @@ def exchange_candidate_lists(lists: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class PeerHints:
-    """Threshold-hint arrays every rank of the node can write (CUDA IPC), two generations.
+    """Threshold-hint arrays every rank of the node can write, two generations.
 
     Rank r's K2 pushes a query's new threshold into the hint array of every peer with a remote
     atomicMax over NVLink, so all shards filter against the best threshold found on ANY shard
     (``qst_score_select_peers``).  Generation g is used by step g mod 2 and cleared (stream-ordered)
     right after the previous step's K2, so a fast rank never pushes into memory that a slow rank is
-    about to clear, and hints of one step never leak into the next (different queries).
+    about to clear, and hints of one step never leak into the next (different queries).  The buffers
+    come from the communicator (CUDA IPC between processes, plain allocations between the threads of
+    an emulated node).
     """
 
-    def __init__(self, rows: int, group, device: torch.device):
-        lib = _lib.load()
-        self.rows, self.group, self.device = rows, group, device
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    def __init__(self, rows: int, comm: Comm, device: torch.device):
+        self.rows, self.comm, self.device = rows, comm, device
         self.gen_bytes = ((rows * 4 + 255) // 256) * 256
         self.step = 0
-        self.local = C.c_void_p()
-        self.peers = []
-        handle = C.create_string_buffer(64)
-        ok = 1
-        with torch.cuda.device(device):
-            if lib.qst_peer_buffer_create(2 * self.gen_bytes, C.byref(self.local), handle) != 0:
-                ok, self.local = 0, C.c_void_p()
-            mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
-            every = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
-            dist.all_gather_into_tensor(every, mine, group=group)
-            every = every.cpu().view(self.world, 64)
-            if ok:
-                for r in range(self.world):
-                    if r == self.rank:
-                        continue
-                    p = C.c_void_p()
-                    if lib.qst_peer_buffer_open(bytes(every[r].tolist()), C.byref(p)) != 0:
-                        ok = 0
-                        break
-                    self.peers.append(p)
-            flag = torch.tensor([ok], dtype=torch.int32, device=device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
-        self.ok = bool(int(flag))
-        if not self.ok:
-            self.close()
+        self.buffers = comm.shared_buffers(2 * self.gen_bytes, device)
+        self.ok = self.buffers is not None
 
     def launch_args(self):
         """(local pointer, ctypes array of peer pointers, n_peers) of the current generation."""
         off = (self.step % 2) * self.gen_bytes
-        arr = (C.c_void_p * max(1, len(self.peers)))(*[C.c_void_p(p.value + off) for p in self.peers])
-        return C.c_void_p(self.local.value + off), arr, len(self.peers)
+        peers = self.buffers.peers
+        arr = (C.c_void_p * max(1, len(peers)))(*[C.c_void_p(p + off) for p in peers])
+        return C.c_void_p(self.buffers.local + off), arr, len(peers)
 
     def advance(self, stream_ptr):
         """Call right after K2 was enqueued: clear the other generation for the next step."""
         nxt = ((self.step + 1) % 2) * self.gen_bytes
-        _lib.check(_lib.load().qst_peer_buffer_clear(self.local, nxt, self.gen_bytes, stream_ptr))
+        _lib.check(_lib.load().qst_peer_buffer_clear(C.c_void_p(self.buffers.local), nxt, self.gen_bytes, stream_ptr))
         self.step += 1
 
     def close(self):
-        lib = _lib.load()
-        for p in self.peers:
-            lib.qst_peer_buffer_close(p)
-        self.peers = []
-        if self.local:
-            lib.qst_peer_buffer_destroy(self.local)
-            self.local = C.c_void_p()
+        if self.buffers is not None:
+            self.buffers.close()
+            self.buffers = None
 
 
 class ShardedCorpus:
-    """This rank's shard of an N-row corpus + the collective top-k over all shards."""
+    """This rank's shard of an N-row corpus + the collective top-k over all shards.
+
+    ``full_master=None`` (default, the partition of BASELINE.json's north star): this rank keeps ITS rows
+    only -- bf16 tensor-core operand AND fp32 master.  ``full_master=<[N, D] tensor>``: the fp32 master is
+    replicated on every rank (3 GB per 1M x 768 rows), only the bf16 operand is sharded.
+    ``comm``: a ``qst_b200.comm.Comm`` (default: ``torch.distributed``'s default group, or a world of one).
+    """
 
     def __init__(self, shard_embeddings: torch.Tensor, n_total: int, score: str = "cos_sim", group=None,
-                 query_tile: int = 16384, full_master: Optional[torch.Tensor] = None):
+                 query_tile: int = 16384, full_master: Optional[torch.Tensor] = None, comm: Optional[Comm] = None):
+        self.comm = comm if comm is not None else default_comm(group)
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world, self.rank = self.comm.world, self.comm.rank
         self.n_total = n_total
         self.score = score
         self.start, self.end = shard_bounds(n_total, self.world, self.rank)
@@ -171,24 +159,55 @@ class ShardedCorpus:
         self._peer_hints_off = bool(os.environ.get("QST_NO_PEER_HINTS"))
         self._timing = [] if os.environ.get("QST_SHARD_TIMING") else None   # debug: per-stage CUDA events
         self.master = None
+        self.last_rescanned = 0      # queries repaired by the distributed exact re-scan in the last call
         if full_master is not None:
             if full_master.shape[0] != n_total:
                 raise ValueError(f"full_master must have {n_total} rows, got {full_master.shape[0]}")
             # norms / residual statistics of the whole corpus for rescoring and the certificate; the
             # bf16 operand is NOT built for it
             self.master = scoring.prepare_rows(full_master, scoring.CORPUS_PREP[score], want_bf16=False)
+            self.global_stats = self.master.stats
+        else:
+            # certificate statistics (max rounding residual, max norm) over ALL shards
+            self.global_stats = self.comm.all_reduce_max(self.index.rows.stats) if self.world > 1 \
+                else self.index.rows.stats
+
+    @property
+    def master_mode(self) -> str:
+        return "replicated" if self.master is not None else "sharded"
+
+    def _ws(self, nbytes: int, tag: str) -> torch.Tensor:
+        # per-rank tags: the ranks of an emulated node (LocalComm) share one device and one stream
+        return scoring._workspace(nbytes, self.index.device, f"{tag}.r{self.rank}")
 
     # ---------------------------------------------------------------------------------------------
-    def topk(self, queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True):
-        """Global exact top-k for every query: (values [Q, k], global ids [Q, k], margins [Q])."""
+    def topk(self, queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True,
+             strategy: str = "owners"):
+        """Global exact top-k for every query, on every rank: (values [Q, k], global ids [Q, k],
+        margins [Q]).  ``strategy="owners"``: the batch is cut into one slice per rank, every rank
+        finalises its slice (``topk_owned``) and the rankings are all-gathered.
+        ``strategy="allgather_merge"``: every rank computes its exact LOCAL top-k of all queries, the
+        lists are all-gathered per query tile and merged (``qst_merge_topk``)."""
         dev = self.index.device
         queries = queries.to(dev)
         if self.world == 1:
             r = scoring.topk(queries, self.index, k, kprime, exact)
             return r.values, r.indices, r.margin
-        if self.master is not None:
-            return self._topk_candidate_exchange(queries, k, kprime, exact)
-        return self._topk_list_exchange(queries, k, kprime, exact)
+        if strategy == "allgather_merge":
+            return self._topk_list_exchange(queries, k, kprime, exact)
+        if strategy != "owners":
+            raise ValueError(f"strategy must be 'owners' or 'allgather_merge', {strategy!r} given")
+        G, Q = self.world, queries.shape[0]
+        q_own = -(-Q // G)
+        q_pad = q_own * G
+        if q_pad != Q:     # pad with copies of the last query so that every rank owns q_own rows
+            queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
+        vals, idx, margin = self.topk_owned(queries[self.rank * q_own:(self.rank + 1) * q_own], k, kprime, exact)
+        with torch.cuda.device(dev):
+            gv, gi, gm = self.comm.all_gather(vals), self.comm.all_gather(idx), self.comm.all_gather(margin)
+            if self._timing:
+                self._mark(self._timing[-1], "all_gather")
+        return gv[:Q], gi[:Q], gm[:Q]
 
     def _hints_for(self, rows: int, dev) -> Optional[PeerHints]:
         """Peer-visible hint arrays for `rows` query rows (collective on first use / growth)."""
@@ -197,11 +216,11 @@ class ShardedCorpus:
         if self._peer_hints is None or self._peer_hints.rows < rows:
             if self._peer_hints is not None:
                 torch.cuda.synchronize(dev)
-                dist.barrier(self.group)          # nobody may still be pushing into the old buffers
+                self.comm.barrier()               # nobody may still be pushing into the old buffers
                 self._peer_hints.close()
-            self._peer_hints = PeerHints(rows, self.group, dev)
+            self._peer_hints = PeerHints(rows, self.comm, dev)
             if not self._peer_hints.ok:
-                self._peer_hints_off = True       # IPC not available here: per-shard thresholds only
+                self._peer_hints_off = True       # no peer-writable memory here: per-shard thresholds only
                 return None
         return self._peer_hints
 
@@ -229,37 +248,166 @@ class ShardedCorpus:
     def timing_report(self) -> str:
         return "  ".join(f"{n} {v:.3f}" for n, v in self.stage_ms().items())
 
-    # ---- master="replicated": lists of bf16 candidates go to the owner of each query -----------
-    def _topk_candidate_exchange(self, queries, k, kprime, exact):
-        """All queries in, all rankings out (every rank): slices the batch by owner, runs
-        ``topk_owned`` and all-gathers the rankings."""
-        dev = self.index.device
-        G = self.world
-        Q = queries.shape[0]
-        q_own = -(-Q // G)
-        q_pad = q_own * G
-        if q_pad != Q:     # pad with copies of the last query so that every rank owns q_own rows
-            queries = torch.cat([queries, queries[-1:].expand(q_pad - Q, -1)])
-        vals, idx, margin = self.topk_owned(queries[self.rank * q_own:(self.rank + 1) * q_own], k, kprime, exact)
-        with torch.cuda.device(dev):
-            gv, gi = all_gather_topk(vals, idx, self.group)                 # [G, q_own, k]
-            gm = torch.empty(q_pad, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(gm, margin, group=self.group)
-            if self._timing:
-                self._mark(self._timing[-1], "all_gather")
-        return gv.view(q_pad, k)[:Q], gi.view(q_pad, k)[:Q], gm[:Q]
-
+    # ---- the data-parallel entry: every rank brings the queries it owns ---------------------------
     def topk_owned(self, own_queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True):
         """Collective: every rank passes ITS OWN slice of the query batch (same number of rows on
         every rank; global query id = rank * rows + i) and gets the exact global top-k of that slice
         back: (values [q_own, k], global ids [q_own, k], margins [q_own]).
 
-        Only the bf16 tensor-core operands of the queries travel between ranks (one all-gather over
-        NVLink); fp32 queries, rescoring and results stay with the owner.  Needs the replicated
-        fp32 master (``full_master=``).
+        Every rank scores all G*q queries against its shard on the tensor cores (K2, thresholds shared
+        between the shards through peer memory), lists its m best candidates per query by bf16 key, and
+        ONE all-to-all routes each query's G lists to the rank that owns the query.  Then
+
+        * sharded master (default): the owner picks the k' best overall and asks each shard for the
+          exact fp32 scores of the rows it holds (``qst_select_requests`` -> all-to-all ->
+          ``qst_rescore_requests`` on the shard, from its own fp32 rows -> all-to-all ->
+          ``qst_finalize_exact``).  The fp32 queries are all-gathered once per call; rescoring work per
+          rank is the same q*k' rows as on one GPU.
+        * replicated master: the owner rescoring-finalises the lists itself from its copy of the whole
+          fp32 corpus (``qst_finalize_lists``); only bf16 query operands travel.
         """
-        if self.master is None:
-            raise _lib.QstError("topk_owned needs ShardedCorpus(full_master=...) (candidate exchange)")
+        if self.master is not None:
+            return self._topk_owned_replicated(own_queries, k, kprime, exact)
+        return self._topk_owned_sharded(own_queries, k, kprime, exact)
+
+    def _select_pass(self, q_bf16, q_pad, k, kprime, marks):
+        """K2 on the local shard for all q_pad queries + the per-query candidate lists by bf16 key.
+        Returns (lists [q_pad, m+1, 2] int32, m, k' of the whole corpus)."""
+        lib = _lib.load()
+        dev = self.index.device
+        G, score = self.world, self.score
+        st = _lib.stream_ptr(dev)
+        # k' of the whole corpus decides how many candidates every shard lists (m); the shard's
+        # own K2 then only has to retain its m best
+        kprime_all = scoring.make_plan(q_pad, self.n_total, self.index.d, k, kprime, score).kprime
+        m = candidates_per_shard(kprime_all, G)
+        plan = scoring.make_plan(q_pad, self.index.n, self.index.d, min(k, m), m, score)
+        hints = self._hints_for(plan.m_tiles * plan.rows_per_unit, dev) if G > 1 else None
+        if hints is not None:
+            # thresholds are shared by the units of ALL shards: size the per-unit retention for
+            # k' of the whole corpus spread over stripes x shards units (same Poisson-tail rule as
+            # qst_topk_plan_make)
+            ku = max(16, -(-(3 * -(-kprime_all // (plan.stripes * G)) + 8) // 8) * 8)
+            _lib.check(lib.qst_topk_plan_set_kunit(C.byref(plan), min(ku, plan.kunit)))
+        ws = self._ws(plan.ws_bytes, "select")
+        if hints is not None:
+            local, peers, n_peers = hints.launch_args()
+            _lib.check(lib.qst_score_select_peers(C.byref(plan), q_bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+                                                  ws.data_ptr(), local, peers, n_peers, st))
+            hints.advance(st)
+        else:
+            _lib.check(lib.qst_score_select(C.byref(plan), q_bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+                                            ws.data_ptr(), st))
+        self._mark(marks, "K2")
+        lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
+        _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
+        self._mark(marks, "select")
+        return lists, m, kprime_all
+
+    # ---- fp32 master sharded: requests to the shards, exact scores back ----------------------------
+    def _topk_owned_sharded(self, own_queries, k, kprime, exact):
+        lib = _lib.load()
+        dev = self.index.device
+        comm, G, r = self.comm, self.world, self.rank
+        own_queries = own_queries.to(dev)
+        q_own = own_queries.shape[0]
+        q_pad = q_own * G
+        score = self.score
+        cos = score == "cos_sim"
+        code = scoring.SCORE_CODES[score]
+        D = self.index.d
+        marks = [] if self._timing is not None else None
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            self._mark(marks, "start")
+            # every rank rescoring rows of ITS shard needs the fp32 queries of all ranks: one
+            # all-gather; K1 then runs on all of them locally (the bf16 operands are not sent)
+            q_all = own_queries.float().contiguous()
+            if G > 1:
+                q_all = comm.all_gather(q_all)
+            pq = scoring.prepare_rows(q_all, scoring.QUERY_PREP[score])
+            self._mark(marks, "gather_q+prep")
+            lists, m, kprime_all = self._select_pass(pq.bf16, q_pad, k, kprime, marks)
+            recv = comm.all_to_all(lists) if G > 1 else lists                     # [G, q_own, m+1, 2]
+            self._mark(marks, "all_to_all")
+            own = slice(r * q_own, (r + 1) * q_own)
+            req = torch.empty((G * q_own, m), dtype=torch.int32, device=dev)      # [G shards, q_own, m]
+            bound = torch.empty(q_own, dtype=torch.int32, device=dev)
+            scratch = self._ws(lib.qst_finalize_lists_scratch_bytes(q_own, G), "lists")
+            _lib.check(lib.qst_select_requests(q_own, G, m, kprime_all, self.n_total, recv.data_ptr(),
+                                               req.data_ptr(), bound.data_ptr(), scratch.data_ptr(), st))
+            self._mark(marks, "requests")
+            req_in = comm.all_to_all(req) if G > 1 else req                       # [G owners, q_own, m]
+            exact_out = torch.empty((G * q_own, m), dtype=torch.float32, device=dev)
+            c = self.index.rows
+            _lib.check(lib.qst_rescore_requests(G * q_own, m, D, code, req_in.data_ptr(), pq.f32.data_ptr(),
+                                                pq.inv_norm.data_ptr() if cos else None, c.f32.data_ptr(),
+                                                c.inv_norm.data_ptr() if cos else None, exact_out.data_ptr(), st))
+            self._mark(marks, "rescore")
+            exact_in = comm.all_to_all(exact_out) if G > 1 else exact_out         # [G shards, q_own, m]
+            vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
+            idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
+            margin = torch.empty(q_own, dtype=torch.float32, device=dev)
+            _lib.check(lib.qst_finalize_exact(q_own, G, m, k, code, D, self.n_total, req.data_ptr(),
+                                              exact_in.data_ptr(), bound.data_ptr(), pq.f32[own].data_ptr(),
+                                              pq.err[own].data_ptr(), self.global_stats.data_ptr(),
+                                              vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), st))
+            self._mark(marks, "replies+finalize")
+            if exact:
+                self._distributed_rescan(pq, q_own, k, vals, idx, margin)
+            self._mark(marks, "rescan")
+            if marks is not None:
+                self._timing.append(marks)
+        return vals, idx, margin
+
+    def _distributed_rescan(self, pq, q_own, k, vals, idx, margin):
+        """Backstop of the sharded-master path: queries whose certificate failed are re-scanned in fp32
+        by EVERY shard against its own rows (``qst_exact_rescan_lists``: rows scoring at least the
+        owner's current k-th exact score), the G lists go back to the owner and are merged.  Needs one
+        host read of "is anything flagged" per call (the single-GPU re-scan is device-driven)."""
+        lib = _lib.load()
+        dev = self.index.device
+        comm, G, r = self.comm, self.world, self.rank
+        cos = self.score == "cos_sim"
+        code = scoring.SCORE_CODES[self.score]
+        st = _lib.stream_ptr(dev)
+        state = torch.stack([margin, vals[:, k - 1]], dim=1).contiguous()             # [q_own, 2]
+        all_state = comm.all_gather(state) if G > 1 else state                         # [G*q_own, 2]
+        flagged = ~(all_state[:, 0] > 0)
+        n_flagged = int(flagged.sum())                                                 # host sync, same on all ranks
+        self.last_rescanned = n_flagged
+        if n_flagged == 0:
+            return
+        kth = all_state[:, 1].contiguous()
+        rank_of = torch.cumsum(flagged.to(torch.int64), 0) - 1                         # 0-based rank among flagged
+        n_rows = G * q_own
+        c = self.index.rows
+        scratch = self._ws(lib.qst_exact_rescan_workspace_bytes(n_rows, k), "rescan")
+        lists_v = torch.full((n_rows, k), float("-inf"), dtype=torch.float32, device=dev)
+        lists_i = torch.full((n_rows, k), -1, dtype=torch.int64, device=dev)
+        overflow = torch.zeros(n_rows, dtype=torch.int32, device=dev)
+        for lo in range(0, n_flagged, 8192):                                           # one pass serves 8192 queries
+            sel = flagged & (rank_of >= lo) & (rank_of < lo + 8192)
+            m_in = torch.where(sel, torch.full_like(kth, -1.0), torch.ones_like(kth))
+            _lib.check(lib.qst_exact_rescan_lists(n_rows, self.index.n, self.index.d, k, code, pq.f32.data_ptr(),
+                                                  pq.inv_norm.data_ptr() if cos else None, c.f32.data_ptr(),
+                                                  c.inv_norm.data_ptr() if cos else None, self.start, kth.data_ptr(),
+                                                  m_in.data_ptr(), lists_v.data_ptr(), lists_i.data_ptr(),
+                                                  overflow.data_ptr(), scratch.data_ptr(), st))
+        if G > 1:
+            lists_v, lists_i = comm.all_to_all(lists_v), comm.all_to_all(lists_i)      # [G shards, q_own, k]
+            overflow = comm.all_to_all(overflow.view(n_rows, 1)).view(G, q_own)
+        else:
+            overflow = overflow.view(1, q_own)
+        mv, mi = merge_topk(lists_v.view(G, q_own, k), lists_i.view(G, q_own, k))
+        mine = flagged[r * q_own:(r + 1) * q_own]
+        vals[mine] = mv[mine]
+        idx[mine] = mi[mine]
+        repaired = torch.where(overflow.amax(dim=0) > 0, torch.zeros_like(margin), torch.full_like(margin, float("inf")))
+        margin[mine] = repaired[mine]
+
+    # ---- fp32 master replicated: lists of bf16 candidates go to the owner of each query -----------
+    def _topk_owned_replicated(self, own_queries, k, kprime, exact):
         lib = _lib.load()
         dev = self.index.device
         G = self.world
@@ -274,44 +422,15 @@ class ShardedCorpus:
             st = _lib.stream_ptr(dev)
             self._mark(marks, "start")
             pq = scoring.prepare_rows(own_queries, scoring.QUERY_PREP[score])
-            if G > 1:
-                q_bf16 = torch.empty((q_pad, pq.bf16.shape[1]), dtype=torch.bfloat16, device=dev)
-                dist.all_gather_into_tensor(q_bf16, pq.bf16, group=self.group)
-            else:
-                q_bf16 = pq.bf16
+            q_bf16 = self.comm.all_gather(pq.bf16) if G > 1 else pq.bf16
             self._mark(marks, "prep+gather_q")
-            # k' of the whole corpus decides how many candidates every shard lists (m); the shard's
-            # own K2 then only has to retain its m best
-            kprime_all = scoring.make_plan(q_pad, self.n_total, self.index.d, k, kprime, score).kprime
-            m = candidates_per_shard(kprime_all, G)
-            plan = scoring.make_plan(q_pad, self.index.n, self.index.d, min(k, m), m, score)
-            hints = self._hints_for(plan.m_tiles * plan.rows_per_unit, dev) if G > 1 else None
-            if hints is not None:
-                # thresholds are shared by the units of ALL shards: size the per-unit retention for
-                # k' of the whole corpus spread over stripes x shards units (same Poisson-tail rule as
-                # qst_topk_plan_make)
-                ku = max(16, -(-(3 * -(-kprime_all // (plan.stripes * G)) + 8) // 8) * 8)
-                _lib.check(lib.qst_topk_plan_set_kunit(C.byref(plan), min(ku, plan.kunit)))
-            ws = scoring._workspace(plan.ws_bytes, dev, "select")
-            if hints is not None:
-                local, peers, n_peers = hints.launch_args()
-                _lib.check(lib.qst_score_select_peers(C.byref(plan), q_bf16.data_ptr(),
-                                                      self.index.rows.bf16.data_ptr(), ws.data_ptr(), local, peers,
-                                                      n_peers, st))
-                hints.advance(st)
-            else:
-                _lib.check(lib.qst_score_select(C.byref(plan), q_bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
-                                                ws.data_ptr(), st))
-            self._mark(marks, "K2")
-            lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
-            _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
-            self._mark(marks, "select")
-            recv = exchange_candidate_lists(lists, self.group) if G > 1 else lists.view(1, q_pad, m + 1, 2)
+            lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks)
+            recv = self.comm.all_to_all(lists) if G > 1 else lists                # [G, q_own, m+1, 2]
             self._mark(marks, "all_to_all")
             vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
             margin = torch.empty(q_own, dtype=torch.float32, device=dev)
-            scratch = scoring._workspace(lib.qst_finalize_lists_scratch_bytes(q_own, G), dev, "lists")
+            scratch = self._ws(lib.qst_finalize_lists_scratch_bytes(q_own, G), "lists")
             mst = self.master
             q_inv = pq.inv_norm if cos else None
             _lib.check(lib.qst_finalize_lists(q_own, G, m, k, kprime_all, code, self.index.d, recv.data_ptr(),
@@ -321,7 +440,7 @@ class ShardedCorpus:
                                               margin.data_ptr(), scratch.data_ptr(), st))
             self._mark(marks, "finalize_lists")
             if exact:
-                rs = scoring._workspace(lib.qst_exact_rescan_workspace_bytes(q_own, k), dev, "rescan")
+                rs = self._ws(lib.qst_exact_rescan_workspace_bytes(q_own, k), "rescan")
                 _lib.check(lib.qst_exact_rescan(q_own, self.n_total, self.index.d, k, code, pq.f32.data_ptr(),
                                                 _lib.ptr(q_inv), mst.f32.data_ptr(),
                                                 mst.inv_norm.data_ptr() if cos else None, 0, vals.data_ptr(),
@@ -331,11 +450,12 @@ class ShardedCorpus:
                 self._timing.append(marks)
         return vals, idx, margin
 
-    # ---- master="sharded": exact per-shard top-k lists, all-gather, merge ---------------------------
+    # ---- literal "local exact top-k, all-gather, merge" (north-star wording; more rescoring work) ----
     def _topk_list_exchange(self, queries, k, kprime, exact):
         dev = self.index.device
         Q = queries.shape[0]
         main = torch.cuda.current_stream(dev)
+        side = self._side if isinstance(self.comm, TorchComm) else main    # emulated ranks share one stream
         out_v: List[torch.Tensor] = []
         out_i: List[torch.Tensor] = []
         margins: List[torch.Tensor] = []
@@ -348,15 +468,19 @@ class ShardedCorpus:
             if pending is not None:           # finish the previous tile's exchange
                 out_v.append(pending[0]); out_i.append(pending[1])
                 main.wait_event(pending[2])
-            with torch.cuda.stream(self._side):
-                self._side.wait_event(done)
-                gv, gi = all_gather_topk(r.values, r.indices, self.group)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                gv = self.comm.all_gather(r.values).view(self.world, -1, k)
+                gi = self.comm.all_gather(r.indices).view(self.world, -1, k)
                 mv, mi = merge_topk(gv, gi)
                 fin = torch.cuda.Event()
-                fin.record(self._side)
+                fin.record(side)
             for t in (r.values, r.indices, gv, gi, mv, mi):
-                t.record_stream(self._side)
+                t.record_stream(side)
             pending = (mv, mi, fin)
         out_v.append(pending[0]); out_i.append(pending[1])
         main.wait_event(pending[2])
-        return torch.cat(out_v), torch.cat(out_i), torch.cat(margins)
+        # a query is certified when every shard certified its local list
+        margin = torch.cat(margins)
+        margin = -self.comm.all_reduce_max(-margin)
+        return torch.cat(out_v), torch.cat(out_i), margin

@@ -55,6 +55,19 @@ def _worker(rank, world, port, out_dir):
                     + 1000 * src)[rank * q_own:(rank + 1) * q_own]
             assert torch.equal(recv[src], want)
         assert sharded.candidates_per_shard(192, 8) == 96 and sharded.candidates_per_shard(192, 1) == 192
+        # the communicator ShardedCorpus talks to (same layouts, torch.distributed underneath)
+        from qst_b200 import comm
+        cm = comm.default_comm()
+        assert isinstance(cm, comm.TorchComm) and cm.world == world and cm.rank == rank
+        x = torch.arange(6, dtype=torch.float32).view(3, 2) + 100 * rank
+        ga = cm.all_gather(x)
+        assert ga.shape == (world * 3, 2) and torch.equal(ga[rank * 3:(rank + 1) * 3], x)
+        assert torch.equal(ga[(1 - rank) * 3:(2 - rank) * 3], x - 100 * rank + 100 * (1 - rank))
+        y = torch.arange(world * 2, dtype=torch.int32).view(world * 2, 1) + 10 * rank      # block r -> rank r
+        a2a = cm.all_to_all(y)
+        for src in range(world):
+            assert torch.equal(a2a[src * 2:(src + 1) * 2, 0], torch.arange(rank * 2, rank * 2 + 2, dtype=torch.int32) + 10 * src)
+        assert torch.equal(cm.all_reduce_max(torch.tensor([float(rank), 5.0 - rank])), torch.tensor([world - 1.0, 5.0]))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -1,5 +1,5 @@
-"""Real multi-GPU run of the corpus-sharded path (NCCL): both exchange strategies against the CPU
-oracle.  Needs >= 2 visible GPUs (`gpurun --gpus 2`), skipped otherwise."""
+"""Real multi-GPU run of the corpus-sharded path (NCCL): sharded and replicated fp32 master, the
+owner and the all-gather/merge strategies, against the CPU oracle.  Needs >= 2 visible GPUs (`gpurun --gpus 2`), skipped otherwise."""
 import os
 import socket
 
@@ -34,24 +34,26 @@ def _worker(rank, world, port, out_dir):
         s, e = sharded.shard_bounds(N, world, rank)
         for full in (None, c.to(dev)):
             corp = sharded.ShardedCorpus(c[s:e].to(dev), N, "cos_sim", query_tile=128, full_master=full)
-            vals, idx, margin = corp.topk(q.to(dev), k)
-            torch.cuda.synchronize()
-            assert vals.shape == (Q, k) and bool((margin > 0).all())
-            torch.testing.assert_close(vals.cpu(), want_val, rtol=0, atol=2e-6)
-            mism = (idx.cpu() != want_idx)
-            # only tie swaps (scores within 1e-6) may differ
-            assert float((vals.cpu()[mism] - want_val[mism]).abs().max() if mism.any() else 0.0) <= 2e-6
-            assert mism.float().mean() < 1e-3
-            if full is not None:
-                # owner-sliced entry: every rank passes its slice, gets its slice of the answer
-                q_own = -(-Q // world)
-                qp = torch.cat([q, q[-1:].expand(q_own * world - Q, -1)])
-                lo, hi = rank * q_own, (rank + 1) * q_own
-                v2, i2, m2 = corp.topk_owned(qp[lo:hi].to(dev), k)
-                hi_real = min(hi, Q)
-                torch.testing.assert_close(v2.cpu()[: hi_real - lo], want_val[lo:hi_real], rtol=0, atol=2e-6)
-                assert (i2.cpu()[: hi_real - lo] != want_idx[lo:hi_real]).float().mean() < 1e-3
-                assert bool((m2 > 0).all())
+            assert corp.master_mode == ("sharded" if full is None else "replicated")
+            strategies = ("owners", "allgather_merge") if full is None else ("owners",)
+            for strategy in strategies:
+                vals, idx, margin = corp.topk(q.to(dev), k, strategy=strategy)
+                torch.cuda.synchronize()
+                assert vals.shape == (Q, k) and bool((margin > 0).all())
+                torch.testing.assert_close(vals.cpu(), want_val, rtol=0, atol=2e-6)
+                mism = (idx.cpu() != want_idx)
+                # only tie swaps (scores within 1e-6) may differ
+                assert float((vals.cpu()[mism] - want_val[mism]).abs().max() if mism.any() else 0.0) <= 2e-6
+                assert mism.float().mean() < 1e-3
+            # owner-sliced entry: every rank passes its slice, gets its slice of the answer
+            q_own = -(-Q // world)
+            qp = torch.cat([q, q[-1:].expand(q_own * world - Q, -1)])
+            lo, hi = rank * q_own, (rank + 1) * q_own
+            v2, i2, m2 = corp.topk_owned(qp[lo:hi].to(dev), k)
+            hi_real = min(hi, Q)
+            torch.testing.assert_close(v2.cpu()[: hi_real - lo], want_val[lo:hi_real], rtol=0, atol=2e-6)
+            assert (i2.cpu()[: hi_real - lo] != want_idx[lo:hi_real]).float().mean() < 1e-3
+            assert bool((m2 > 0).all())
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,105 @@
+"""The corpus-sharded code path itself (``ShardedCorpus.topk`` / ``topk_owned``, both master modes and
+the all-gather/merge strategy) on ONE GPU: the G ranks are G threads of this process, the collectives
+go through ``qst_b200.comm.LocalComm`` (tensor copies behind a barrier), the peer-writable threshold
+hints are plain allocations.  Everything else -- K1, K2 with shared thresholds, candidate lists, the
+request / rescore / finalize kernels, the distributed exact re-scan -- is the code the multi-GPU run
+executes.  Compared with the CPU oracle of the UNSHARDED corpus."""
+import pytest
+import torch
+
+from test_gpu_scoring import _oracle_topk, assert_same_ranking
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _run(G, q, c, k, score, master, strategy="owners", owned=False, query_tile=16384):
+    """All ranks of an emulated node; returns rank-ordered (vals, idx, margin, rescanned)."""
+    import qst_b200
+    from qst_b200 import comm, sharded
+    N = c.shape[0]
+    dev = _dev()
+    q_dev, c_dev = q.to(dev), c.to(dev)
+
+    def body(cm):
+        s, e = sharded.shard_bounds(N, cm.world, cm.rank)
+        corp = sharded.ShardedCorpus(c_dev[s:e], N, score, comm=cm, query_tile=query_tile,
+                                     full_master=c_dev if master == "replicated" else None)
+        assert corp.master_mode == master and corp.world == G and corp.rank == cm.rank
+        if owned:
+            q_own = -(-q.shape[0] // G)
+            qp = torch.cat([q_dev, q_dev[-1:].expand(q_own * G - q.shape[0], -1)])
+            v, i, m = corp.topk_owned(qp[cm.rank * q_own:(cm.rank + 1) * q_own], k)
+        else:
+            v, i, m = corp.topk(q_dev, k, strategy=strategy)
+        torch.cuda.synchronize()
+        return v.cpu(), i.cpu(), m.cpu(), corp.last_rescanned
+
+    return comm.run_local_world(G, body)
+
+
+@pytest.mark.parametrize("score", ["cos_sim", "dot_score", "euclid_score"])
+@pytest.mark.parametrize("G,master", [(2, "sharded"), (4, "sharded"), (3, "sharded"), (4, "replicated")])
+def test_sharded_topk_matches_unsharded_oracle(G, master, score):
+    g = torch.Generator().manual_seed(100 + G)
+    Q, N, D, k = 150, 30011, 96, 50
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g) * (1 + torch.rand(N, 1, generator=g))
+    want_val, want_idx = _oracle_topk(q, c, k, score)
+    out = _run(G, q, c, k, score, master)
+    for rank, (v, i, m, _) in enumerate(out):
+        what = f"G={G} {master} {score} rank {rank}"
+        assert v.shape == (Q, k) and i.shape == (Q, k)
+        assert bool((m > 0).all()), what
+        if score == "dot_score":
+            scale = float(want_val.abs().max())
+            assert_same_ranking(i, v / scale, want_idx, want_val / scale, what)
+        else:
+            assert_same_ranking(i, v, want_idx, want_val, what, truth=(q, c, score) if score == "euclid_score" else None)
+    # every rank holds the same answer
+    for v, i, m, _ in out[1:]:
+        assert torch.equal(v, out[0][0]) and torch.equal(i, out[0][1])
+
+
+def test_owned_slices_and_allgather_merge_strategy():
+    """``topk_owned`` returns exactly the owner's slice; the literal local-top-k / all-gather / merge
+    strategy gives the same ranking."""
+    g = torch.Generator().manual_seed(7)
+    Q, N, D, k, G = 101, 20000, 64, 20, 4
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, k, "cos_sim")
+    q_own = -(-Q // G)
+    for master in ("sharded", "replicated"):
+        out = _run(G, q, c, k, "cos_sim", master, owned=True)
+        for rank, (v, i, m, _) in enumerate(out):
+            lo, hi = rank * q_own, min((rank + 1) * q_own, Q)
+            assert v.shape == (q_own, k)
+            assert_same_ranking(i[:hi - lo], v[:hi - lo], want_idx[lo:hi], want_val[lo:hi], f"{master} owned rank {rank}")
+            assert bool((m > 0).all())
+    out = _run(G, q, c, k, "cos_sim", "sharded", strategy="allgather_merge", query_tile=40)
+    for rank, (v, i, m, _) in enumerate(out):
+        assert_same_ranking(i, v, want_idx, want_val, f"allgather_merge rank {rank}")
+        assert bool((m > 0).all())
+
+
+@pytest.mark.parametrize("master", ["sharded", "replicated"])
+def test_sharded_near_ties_go_through_the_exact_rescan(master):
+    """Clustered corpus (centroid + tiny noise): the bf16 pass cannot separate neighbours, certificates
+    fail, and the exact re-scan -- distributed over the shards when the master is sharded -- must
+    still deliver the oracle's ranking."""
+    g = torch.Generator().manual_seed(3)
+    Q, N, D, k, G = 40, 6000, 64, 10, 3
+    cent = torch.randn(30, D, generator=g)
+    c = cent[torch.randint(0, 30, (N,), generator=g)] + 1e-4 * torch.randn(N, D, generator=g)
+    q = cent[torch.randint(0, 30, (Q,), generator=g)] + 1e-3 * torch.randn(Q, D, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, k, "cos_sim")
+    out = _run(G, q, c, k, "cos_sim", master)
+    for rank, (v, i, m, rescanned) in enumerate(out):
+        assert_same_ranking(i, v, want_idx, want_val, f"near ties {master} rank {rank}")
+        assert bool((m > 0).all())
+    if master == "sharded":
+        assert out[0][3] > 0, "this data is meant to fail certificates and exercise the distributed re-scan"

@@ -201,3 +201,40 @@ def test_loss_evaluator_instance_shapes():
     with pytest.raises(ValueError):
         le._texts_of(["a", "b", "c"])
     assert [len(b) for b in le._batches(range(10), 4)] == [4, 4, 2]
+
+
+def test_local_comm_collectives_have_the_layouts_of_the_distributed_ones():
+    """``LocalComm`` (G ranks = G threads of one process; used by the single-GPU tests of the sharded
+    path) must lay tensors out exactly like ``TorchComm``: all-gather rank-major, all-to-all source-major."""
+    import torch
+    from qst_b200 import comm
+
+    def body(cm):
+        x = torch.arange(6, dtype=torch.float32).view(3, 2) + 100 * cm.rank
+        ga = cm.all_gather(x)
+        y = torch.arange(cm.world * 2, dtype=torch.int32).view(cm.world * 2, 1) + 10 * cm.rank
+        a2a = cm.all_to_all(y)
+        mx = cm.all_reduce_max(torch.tensor([float(cm.rank), 5.0 - cm.rank]))
+        cm.barrier()
+        return ga, a2a, mx
+
+    world = 3
+    out = comm.run_local_world(world, body)
+    for rank, (ga, a2a, mx) in enumerate(out):
+        assert ga.shape == (world * 3, 2)
+        for src in range(world):
+            assert torch.equal(ga[src * 3:(src + 1) * 3], torch.arange(6, dtype=torch.float32).view(3, 2) + 100 * src)
+            assert torch.equal(a2a[src * 2:(src + 1) * 2, 0],
+                               torch.arange(rank * 2, rank * 2 + 2, dtype=torch.int32) + 10 * src)
+        assert torch.equal(mx, torch.tensor([world - 1.0, 5.0]))
+    # an exception on one rank surfaces instead of dead-locking the others
+    def bad(cm):
+        if cm.rank == 1:
+            raise ValueError("boom")
+        cm.barrier()
+
+    with pytest.raises(ValueError):
+        comm.run_local_world(2, bad)
+    one = comm.SingleComm()
+    t = torch.ones(2)
+    assert one.all_gather(t) is t and one.all_to_all(t) is t and one.world == 1
