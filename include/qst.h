@@ -312,6 +312,44 @@ int qst_merge_topk(const float* vals, const int64_t* idx, int G, int64_t Q, int 
                    float* out_val, int64_t* out_idx, qst_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Collectives of the corpus-sharded path: NCCL over NVLink / NVSwitch, called
+ * directly (libnccl.so.2 is resolved with dlopen at first use; the copy already loaded in the process
+ * is reused).  One communicator per process and device; qst_comm_init is collective.  The unique id
+ * (128 bytes) is created on one rank and distributed by the caller (file, socket, MPI, torch.distributed
+ * ...).  Every call is stream-ordered.  What the exchanges replace is the sequential corpus chunk loop
+ * of ir_evauation_script.py:161, cut in space instead of time.
+ *
+ * Sharded top-k from C, per rank (G ranks, q_own queries owned by each, all buffers on the device):
+ *   qst_prep_rows (own queries) -> qst_comm_allgather (fp32 queries) -> qst_prep_rows (all G*q_own) ->
+ *   qst_topk_plan_make / qst_score_select[_peers] -> qst_select_candidates -> qst_exchange_candidates ->
+ *   qst_select_requests -> qst_comm_alltoall (requests) -> qst_rescore_requests -> qst_comm_alltoall
+ *   (exact scores) -> qst_finalize_exact  [-> qst_exact_rescan_lists + qst_comm_alltoall + qst_merge_topk
+ *   for queries left uncertified];  or, list exchange: qst_finalize_topk locally -> qst_allgather_topk ->
+ *   qst_merge_topk.
+ * ------------------------------------------------------------------------------------------ */
+#define QST_COMM_ID_BYTES 128
+typedef struct qst_comm qst_comm;
+int qst_comm_available(void);      /* 1 when libnccl.so.2 could be loaded */
+int qst_comm_nccl_version(void);   /* e.g. 22809, 0 when unavailable */
+int qst_comm_unique_id(unsigned char* id128);
+int qst_comm_init(const unsigned char* id128, int world, int rank, qst_comm** out);
+int qst_comm_destroy(qst_comm* comm);
+int qst_comm_world(const qst_comm* comm);
+int qst_comm_rank(const qst_comm* comm);
+/* recv [world * bytes_per_rank]: rank-major concatenation of every rank's `send`. */
+int qst_comm_allgather(qst_comm* comm, const void* send, void* recv, size_t bytes_per_rank, qst_stream_t stream);
+/* block r of send (bytes_per_peer bytes) goes to rank r; block r of recv came from rank r. */
+int qst_comm_alltoall(qst_comm* comm, const void* send, void* recv, size_t bytes_per_peer, qst_stream_t stream);
+int qst_comm_allreduce_max_f32(qst_comm* comm, const float* send, float* recv, size_t n, qst_stream_t stream);
+/* K6's exchange: vals/idx [Q, k] per rank -> out [G, Q, k] on every rank (then qst_merge_topk). */
+int qst_allgather_topk(qst_comm* comm, const float* vals, const int64_t* idx, int64_t Q, int k,
+                       float* out_vals, int64_t* out_idx, qst_stream_t stream);
+/* candidate lists of qst_select_candidates over all G * q_own queries (grouped by owner rank) ->
+ * recv [G, q_own, m + 1]: the G shards' lists of the queries this rank owns. */
+int qst_exchange_candidates(qst_comm* comm, const void* lists, void* recv, int64_t q_own, int m,
+                            qst_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K4  IR metrics.  Replaces InformationRetrievalEvaluator.compute_metrics / compute_dcg_at_k
  * [sentence-transformers 2.2.2] (Python float64 loops; 5.9 s of 6.7 s at the script's default
  * k-lists) for rankings that are already on the device.

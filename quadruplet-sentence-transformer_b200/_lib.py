@@ -89,6 +89,18 @@ SIGNATURES = {
     "qst_exact_rescan_workspace_bytes": (C.c_size_t, [_I64, _INT]),
     "qst_exact_rescan": (_INT, [_I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "qst_merge_topk": (_INT, [_P, _P, _INT, _I64, _INT, _P, _P, _P]),
+    "qst_comm_available": (_INT, []),
+    "qst_comm_nccl_version": (_INT, []),
+    "qst_comm_unique_id": (_INT, [C.c_char_p]),
+    "qst_comm_init": (_INT, [C.c_char_p, _INT, _INT, C.POINTER(_P)]),
+    "qst_comm_destroy": (_INT, [_P]),
+    "qst_comm_world": (_INT, [_P]),
+    "qst_comm_rank": (_INT, [_P]),
+    "qst_comm_allgather": (_INT, [_P, _P, _P, C.c_size_t, _P]),
+    "qst_comm_alltoall": (_INT, [_P, _P, _P, C.c_size_t, _P]),
+    "qst_comm_allreduce_max_f32": (_INT, [_P, _P, _P, C.c_size_t, _P]),
+    "qst_allgather_topk": (_INT, [_P, _P, _P, _I64, _INT, _P, _P, _P]),
+    "qst_exchange_candidates": (_INT, [_P, _P, _P, _I64, _INT, _P]),
     "qst_ir_metrics": (_INT, [_P, _I64, _INT, _P, _P, _P, _INT, _P, _P, _P, _P]),
 }
 

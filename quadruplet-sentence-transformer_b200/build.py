@@ -17,7 +17,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libqst.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["common.cu", "quad_loss.cu", "quad_eval.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu"]
+SOURCES = ["common.cu", "quad_loss.cu", "quad_eval.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu",
+           "comm.cu"]
 HEADERS = ["qst_common.cuh", "sm100_ptx.cuh"]
 
 NVCC_FLAGS = [
@@ -72,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -106,40 +106,112 @@ class TorchComm(Comm):
         self._dist.barrier(self.group)
 
     def shared_buffers(self, nbytes, device):
-        """cudaMalloc + CUDA IPC handles exchanged with an all-gather; all ranks or none."""
-        if torch.device(device).type != "cuda":
-            return None
+        return _ipc_shared_buffers(self, nbytes, device)
+
+
+def _ipc_shared_buffers(cm: "Comm", nbytes: int, device) -> Optional[SharedBuffers]:
+    """cudaMalloc + CUDA IPC handles exchanged through ``cm``'s own all-gather; all ranks or none."""
+    if torch.device(device).type != "cuda":
+        return None
+    lib = _lib.load()
+    local, peers, ok = C.c_void_p(), [], 1
+    handle = C.create_string_buffer(64)
+    with torch.cuda.device(device):
+        if lib.qst_peer_buffer_create(nbytes, C.byref(local), handle) != 0:
+            ok, local = 0, C.c_void_p()
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+        every = cm.all_gather(mine).cpu().view(cm.world, 64)
+        if ok:
+            for r in range(cm.world):
+                if r == cm.rank:
+                    continue
+                p = C.c_void_p()
+                if lib.qst_peer_buffer_open(bytes(every[r].tolist()), C.byref(p)) != 0:
+                    ok = 0
+                    break
+                peers.append(p)
+        failed = cm.all_reduce_max(torch.tensor([1.0 - ok], dtype=torch.float32, device=device))
+
+    def closer():
+        for p in peers:
+            lib.qst_peer_buffer_close(p)
+        if local:
+            lib.qst_peer_buffer_destroy(local)
+
+    if float(failed) > 0:
+        closer()
+        return None
+    return SharedBuffers(local.value, [p.value for p in peers], closer)
+
+
+class NcclComm(Comm):
+    """NCCL through the C ABI (``qst_comm_*``): no ``torch.distributed`` on the data path.  The 128-byte
+    unique id is made on one rank (``NcclComm.unique_id()``) and handed to all of them by the caller;
+    ``NcclComm.from_torch`` borrows an initialised ``torch.distributed`` group just for that hand-over."""
+
+    def __init__(self, world: int, rank: int, unique_id: bytes, device: torch.device):
         lib = _lib.load()
-        dist = self._dist
-        local, peers, ok = C.c_void_p(), [], 1
-        handle = C.create_string_buffer(64)
-        with torch.cuda.device(device):
-            if lib.qst_peer_buffer_create(nbytes, C.byref(local), handle) != 0:
-                ok, local = 0, C.c_void_p()
-            mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
-            every = self.all_gather(mine).cpu().view(self.world, 64)
-            if ok:
-                for r in range(self.world):
-                    if r == self.rank:
-                        continue
-                    p = C.c_void_p()
-                    if lib.qst_peer_buffer_open(bytes(every[r].tolist()), C.byref(p)) != 0:
-                        ok = 0
-                        break
-                    peers.append(p)
-            flag = torch.tensor([ok], dtype=torch.int32, device=device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if not lib.qst_comm_available():
+            raise _lib.QstError("libnccl.so.2 could not be loaded: the C-ABI communicator is unavailable")
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of NcclComm.unique_id()")
+        self.world, self.rank, self.device = world, rank, torch.device(device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.qst_comm_init(bytes(unique_id), world, rank, C.byref(self._h)))
 
-        def closer():
-            for p in peers:
-                lib.qst_peer_buffer_close(p)
-            if local:
-                lib.qst_peer_buffer_destroy(local)
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().qst_comm_unique_id(buf))
+        return buf.raw
 
-        if not bool(int(flag)):
-            closer()
-            return None
-        return SharedBuffers(local.value, [p.value for p in peers], closer)
+    @classmethod
+    def from_torch(cls, device: torch.device, group=None) -> "NcclComm":
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(world, rank, box[0], device)
+
+    def _st(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def all_gather(self, t):
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().qst_comm_allgather(self._h, t.data_ptr(), out.data_ptr(), t.numel() * t.element_size(),
+                                                      self._st()))
+        return out
+
+    def all_to_all(self, t):
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().qst_comm_alltoall(self._h, t.data_ptr(), out.data_ptr(),
+                                                     t.numel() * t.element_size() // self.world, self._st()))
+        return out
+
+    def all_reduce_max(self, t):
+        src = t.to(torch.float32).contiguous()
+        out = torch.empty_like(src)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().qst_comm_allreduce_max_f32(self._h, src.data_ptr(), out.data_ptr(), src.numel(),
+                                                              self._st()))
+        return out.to(t.dtype)
+
+    def barrier(self):
+        self.all_reduce_max(torch.zeros(1, device=self.device))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def shared_buffers(self, nbytes, device):
+        return _ipc_shared_buffers(self, nbytes, device)
+
+    def close(self):
+        if self._h:
+            _lib.load().qst_comm_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 class _LocalWorld:

@@ -30,18 +30,26 @@ from .scoring import cos_sim, dot_score, euclidean_score
 logger = logging.getLogger(__name__)
 
 
-def load_ir_evaluation_set(path: str):
+def load_ir_evaluation_set(path: str, reference_compatible: bool = False):
     """IR evaluation set written by ``create_ir_evaluation_set``
     (``/root/reference/models/evaluators.py:438-442, 521-527``): JSON with ``queries`` {qid: text},
     ``corpus`` {cid: text}, ``relevant`` {qid: [cid, ...]} and ``random_seed``.  Returns
     ``(queries, corpus, relevant_docs)`` with the relevant lists turned into sets, which is what the
-    evaluator expects.  (The reference's own reload at ``models/evaluators.py:556-557`` /
-    ``ir_evauation_script.py:95-96`` does ``set(evaluation_queries["relevant"])`` -- the set of ALL query
-    ids -- for every query; this loader applies the evident intent, ``set(relevant[q])``.)
+    evaluator expects.
+
+    The reference's own reload (``models/evaluators.py:556-557``, ``ir_evauation_script.py:94-96``) does
+    ``relevant[q] = set(evaluation_queries["relevant"])`` -- the set of all QUERY ids, the same for every
+    query -- instead of ``set(relevant[q])``.  The default here applies the evident intent;
+    ``reference_compatible=True`` reproduces the reference's reload literally, so that an evaluation of a
+    reloaded set gives the numbers the reference's script gives on the same file.
     """
     with open(path, "r") as fp:
         data = json.load(fp)
-    relevant = {q: set(docs) for q, docs in data["relevant"].items()}
+    if reference_compatible:
+        every_query_id = set(data["relevant"])
+        relevant = {q: set(every_query_id) for q in data["relevant"]}
+    else:
+        relevant = {q: set(docs) for q, docs in data["relevant"].items()}
     return data["queries"], data["corpus"], relevant
 
 
@@ -109,6 +117,7 @@ class InformationRetrievalEvaluator:
             self._relevant_positions.append(row)
         self._csr_cache = {}
         self.last_margins = {}
+        self.last_uncertified = {}
 
     def _columns(self, fn: str) -> List[str]:
         cols = ["{}-Accuracy@{}".format(fn, k) for k in self.accuracy_at_k]
@@ -228,9 +237,20 @@ class InformationRetrievalEvaluator:
         logger.info("Queries: {}".format(len(self.queries)))
         logger.info("Corpus: {}\n".format(len(self.corpus)))
         scores = {}
+        self.last_uncertified = {}
         for fn_name, res in ranked.items():
             self.last_margins[fn_name] = res.margin
             scores[fn_name] = self.compute_metrics_from_ranking(res.indices)
+            # the metrics have just been read back, so this costs no extra synchronisation: a query can
+            # only be left uncertified when more than 2048 documents tie at or above its k-th score
+            # (qst_exact_rescan's collection limit) -- say so instead of reporting "exact" silently
+            n_bad = int((~(res.margin > 0)).sum())
+            self.last_uncertified[fn_name] = n_bad
+            if n_bad:
+                import warnings
+                warnings.warn(f"{fn_name}: {n_bad} of {res.margin.numel()} queries have no exactness certificate "
+                              f"(more than 2048 documents tied at their k-th score); their rankings are the "
+                              f"tensor-core candidates' and may differ from the fp32 reference inside the tie")
         for fn_name in self.score_function_names:
             logger.info("Score-Function: {}".format(fn_name))
             self.output_scores(scores[fn_name])

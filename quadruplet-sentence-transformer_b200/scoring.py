@@ -11,6 +11,7 @@ Nothing here falls back to PyTorch arithmetic: CPU tensors raise, a missing ``li
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -141,7 +142,9 @@ _ws_cache = {}
 
 
 def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
-    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
+    # one buffer per (purpose, device, stream, host thread): work queued by different host threads on
+    # the same stream interleaves in submission order, so they must not share scratch memory
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
@@ -175,7 +178,12 @@ def topk(queries: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0, exa
     """Exact top-``k`` corpus rows per query under ``index.score``.
 
     bf16 tensor-core pass keeps ``kprime`` candidates per query, fp32 rescoring orders them; with
-    ``exact=True`` queries whose certificate fails are re-scanned in fp32 on the device.
+    ``exact=True`` queries whose certificate fails are re-scanned in fp32 on the device -- all of them
+    (the re-scan queues as many passes of 8192 queries as the batch could need).  ``margin > 0`` marks a
+    proven-exact row; the only way a row comes back with ``margin == 0`` is more than 2048 documents
+    tied at or above its k-th score.  Nothing is read back here (the call is asynchronous); callers that
+    hand rankings to a user check the margins where they synchronise anyway
+    (``InformationRetrievalEvaluator.last_uncertified``).
     """
     lib = _lib.load()
     pq = prepared_queries if prepared_queries is not None else prepare_rows(queries, QUERY_PREP[index.score])
@@ -256,27 +264,34 @@ def _dense_scores(a, b, score: str) -> torch.Tensor:
 _pinned_cache = {}
 
 
-def _pinned_outputs(shape):
-    """Reusable pinned host buffers for the ranking (allocating pinned memory costs milliseconds)."""
-    buf = _pinned_cache.get(shape)
+def _pinned_outputs(shape, device: torch.device):
+    """Reusable pinned host buffers for the ranking (allocating pinned memory costs milliseconds), one
+    pair per (device, stream, shape)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, shape)
+    buf = _pinned_cache.get(key)
     if buf is None:
         buf = (torch.empty(shape, dtype=torch.float32, pin_memory=True),
                torch.empty(shape, dtype=torch.int64, pin_memory=True))
-        _pinned_cache[shape] = buf
+        _pinned_cache[key] = buf
     return buf
 
 
 def topk_host(queries_host: torch.Tensor, index: CorpusIndex, k: int, kprime: int = 0,
-              exact: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+              exact: bool = True, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
     """End-to-end call with HOST buffers: pinned queries in, pinned (values, indices) out.
 
     This is the boundary ``bench.py`` times as ``e2e``: H2D copy of the query embeddings, K1 on the
     queries, K2, K3, D2H copy of the ranking.
+
+    The returned tensors are REUSED pinned buffers (one pair per device, stream and result shape): the
+    next ``topk_host`` call with the same shape on the same stream overwrites them -- ``clone()`` what
+    has to outlive that call, or pass ``out=(values, indices)`` pinned tensors of your own.
     """
     dev = index.device
     q_dev = queries_host.to(dev, non_blocking=True)
     res = topk(q_dev, index, k, kprime, exact)
-    vals, idx = _pinned_outputs(tuple(res.values.shape))
+    vals, idx = out if out is not None else _pinned_outputs(tuple(res.values.shape), dev)
     vals.copy_(res.values, non_blocking=True)
     idx.copy_(res.indices, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()

@@ -484,3 +484,101 @@ class ShardedCorpus:
         margin = torch.cat(margins)
         margin = -self.comm.all_reduce_max(-margin)
         return torch.cat(out_v), torch.cat(out_i), margin
+
+
+class ShardedHostPipeline:
+    """Back-to-back ``topk_owned`` steps with HOST buffers on every rank, double-buffered (the sharded
+    counterpart of ``scoring.HostTopkPipeline``).
+
+    Per step and rank: pinned fp32 queries of the rank's slice in, K1 / K2 / exchanges / exact
+    rescoring, pinned (values, indices) of that slice out.  Every slot owns a CUDA stream and pinned
+    result buffers, so the H2D copy of step i+1 and the D2H copy of step i-1 run on the copy engines
+    while the kernels and collectives of step i occupy the SMs and NVLink.  The kernels of consecutive
+    steps are chained by an event (K2 fills the machine anyway, and the two generations of the
+    peer-shared threshold hints assume steps in order).  Collective: all ranks call ``submit`` the same
+    number of times.
+    """
+
+    def __init__(self, corp: ShardedCorpus, k: int, kprime: int = 0, exact: bool = True, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.corp, self.k, self.kprime, self.exact = corp, k, kprime, exact
+        dev = corp.index.device
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        for st in self._streams:
+            st.wait_stream(torch.cuda.current_stream(dev))
+        self._done = [None] * depth        # slot fully finished (results on the host)
+        self._out = [None] * depth
+        self._keep = [None] * depth
+        self._kernels = None               # event: kernels of the most recent step have been queued and run
+        self._next = 0
+
+    def submit(self, own_queries_host: torch.Tensor) -> int:
+        slot = self._next % len(self._streams)
+        if self._done[slot] is not None:
+            self._done[slot].synchronize()
+        dev = self.corp.index.device
+        st = self._streams[slot]
+        with torch.cuda.stream(st):
+            q_dev = own_queries_host.to(dev, non_blocking=True)      # overlaps the previous step's kernels
+            if self._kernels is not None:
+                st.wait_event(self._kernels)
+            # the distributed exact re-scan needs a host decision ("is anything flagged, anywhere?"),
+            # which would stall the pipeline every step: run the first pass only, ship the global flag
+            # to the host with the results, and repair in result() in the (rare) case it is set
+            deferred = self.exact and self.corp.master is None and self.corp.world > 1
+            vals, idx, margin = self.corp.topk_owned(q_dev, self.k, self.kprime, self.exact and not deferred)
+            flag = None
+            if deferred:
+                flag = self.corp.comm.all_reduce_max((~(margin > 0)).any().to(torch.float32).view(1))
+            ev_k = torch.cuda.Event()
+            ev_k.record(st)
+            shape = tuple(vals.shape)
+            if self._out[slot] is None or tuple(self._out[slot][0].shape) != shape:
+                self._out[slot] = (torch.empty(shape, dtype=torch.float32, pin_memory=True),
+                                   torch.empty(shape, dtype=torch.int64, pin_memory=True),
+                                   torch.zeros(1, dtype=torch.float32, pin_memory=True))
+            self._out[slot][0].copy_(vals, non_blocking=True)
+            self._out[slot][1].copy_(idx, non_blocking=True)
+            if flag is not None:
+                self._out[slot][2].copy_(flag, non_blocking=True)
+            else:
+                self._out[slot][2].zero_()
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._kernels, self._done[slot] = ev_k, ev
+        self._keep[slot] = (q_dev, vals, idx, margin)
+        ticket = self._next
+        self._next += 1
+        return ticket
+
+    def result(self, ticket: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if not (self._next - len(self._streams) <= ticket < self._next):
+            raise ValueError(f"ticket {ticket} is not in flight (next {self._next}, depth {len(self._streams)})")
+        slot = ticket % len(self._streams)
+        self._done[slot].synchronize()
+        out = self._out[slot]
+        if float(out[2][0]) > 0:
+            # some rank holds an uncertified query: every rank sees the same flag and repeats the step
+            # with the exact re-scan, synchronously (collective)
+            st = self._streams[slot]
+            with torch.cuda.stream(st):
+                if self._kernels is not None:
+                    st.wait_event(self._kernels)
+                vals, idx, _ = self.corp.topk_owned(self._keep[slot][0], self.k, self.kprime, True)
+                out[0].copy_(vals, non_blocking=True)
+                out[1].copy_(idx, non_blocking=True)
+                self._kernels = torch.cuda.Event()
+                self._kernels.record(st)
+            st.synchronize()
+            out[2].zero_()
+        return out[0], out[1]
+
+    @property
+    def streams(self):
+        return list(self._streams)
+
+    def drain(self):
+        for ev in self._done:
+            if ev is not None:
+                ev.synchronize()

@@ -54,6 +54,21 @@ def _worker(rank, world, port, out_dir):
             torch.testing.assert_close(v2.cpu()[: hi_real - lo], want_val[lo:hi_real], rtol=0, atol=2e-6)
             assert (i2.cpu()[: hi_real - lo] != want_idx[lo:hi_real]).float().mean() < 1e-3
             assert bool((m2 > 0).all())
+        # the same retrieval with NCCL called through the C ABI (qst_comm_*), no torch.distributed on the data path
+        from qst_b200 import comm
+        nc = comm.NcclComm.from_torch(dev)
+        x = torch.arange(6, dtype=torch.float32, device=dev).view(3, 2) + 100 * rank
+        assert torch.equal(nc.all_gather(x), comm.TorchComm().all_gather(x))
+        y = torch.arange(world * 4, dtype=torch.int32, device=dev).view(world * 2, 2) + 10 * rank
+        assert torch.equal(nc.all_to_all(y), comm.TorchComm().all_to_all(y))
+        assert torch.equal(nc.all_reduce_max(torch.tensor([float(rank), 3.0 - rank], device=dev)).cpu(),
+                           torch.tensor([world - 1.0, 3.0]))
+        corp = sharded.ShardedCorpus(c[s:e].to(dev), N, "cos_sim", comm=nc)
+        vals, idx, margin = corp.topk(q.to(dev), k)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(vals.cpu(), want_val, rtol=0, atol=2e-6)
+        assert (idx.cpu() != want_idx).float().mean() < 1e-3 and bool((margin > 0).all())
+        nc.close()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -34,14 +34,21 @@ def _fp64_scores(q, c, idx, score):
     return 1 / (1 + (qq[:, None, :] - cc).norm(dim=2))
 
 
-def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=None):
+ARBITRATIONS = []   # every time the float64 arbitration below let a run continue (euclid_score only)
+
+
+def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=None, scale=1.0):
     """Index-for-index equality, except inside groups of reference scores within TIE.
-    `truth` = (q, c, score) lets a value mismatch say WHICH side disagrees with float64."""
-    got_idx, got_val = got_idx.cpu(), got_val.cpu()
-    if truth is not None and not torch.allclose(got_val, want_val, rtol=0, atol=2e-6):
-        # arbitration by float64: the fp32 CPU oracle is only a stand-in for the exact scores.  If OUR
-        # values are off, fail with the evidence; if ours agree with float64 and the oracle's do not
-        # (seen twice in ~100 runs on the GPU boxes' hosts, cause unknown), say so loudly and go on
+    ``scale``: scores are compared after division by it (dot_score: ties within 1e-6 RELATIVE to the
+    largest score of the batch, the scale at which fp32 dot products of unnormalised rows agree).
+    ``truth`` = (q, c, "euclid_score") enables the float64 arbitration of a VALUE mismatch, for
+    euclid_score only: the reference computes it through torch.cdist's matmul formulation, which on the
+    host is less accurate than summing (q-c)^2 directly; everywhere else a value mismatch fails."""
+    got_idx, got_val = got_idx.cpu(), got_val.cpu() / scale
+    want_val = want_val / scale
+    if truth is not None and truth[2] == "euclid_score" and not torch.allclose(got_val, want_val, rtol=0, atol=2e-6):
+        # If OUR values are off, fail with the evidence; if ours agree with float64 and the oracle's do
+        # not (seen twice in ~100 runs on the GPU boxes' hosts), say so loudly, record it, and go on
         # with the float64 scores of the oracle's own ranking.
         q, c, score = truth
         rows = ((got_val - want_val).abs() > 2e-6).any(dim=1).nonzero().flatten()
@@ -56,6 +63,7 @@ def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=Non
         import warnings
         warnings.warn("CPU ORACLE DISAGREES WITH FLOAT64 (ours agrees): " + report)
         print("CPU ORACLE DISAGREES WITH FLOAT64 (ours agrees): " + report)
+        ARBITRATIONS.append(report)
         want_val = want_val.clone()
         want_val[rows] = t_want.float()
     torch.testing.assert_close(got_val, want_val, rtol=0, atol=2e-6, msg=lambda m: f"{what} scores: {m}")
@@ -121,14 +129,12 @@ def test_topk_matches_oracle(Q, N, D, k, score, ctas):
     index = qst_b200.CorpusIndex(c.to(_dev()), score)
     res = qst_b200.topk(q.to(_dev()), index, k)
     assert res.plan.ctas == ctas
-    if score == "dot_score":
-        scale = float(want_val.abs().max())
-        torch.testing.assert_close(res.values.cpu() / scale, want_val / scale, rtol=0, atol=2e-6)
-        assert (res.indices.cpu() == want_idx).float().mean() > 0.999
-    else:
-        assert_same_ranking(res.indices, res.values, want_idx, want_val, f"{score} {Q}x{N}x{D} k={k}",
-                            truth=(q, c, score))
+    # dot_score: unnormalised rows, so "ties within 1e-6" is meant relative to the batch's largest score
+    scale = float(want_val.abs().max()) if score == "dot_score" else 1.0
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, f"{score} {Q}x{N}x{D} k={k}",
+                        truth=(q, c, score), scale=scale)
     assert bool((res.margin > 0).all()), "every query must end certified (after the exact re-scan if needed)"
+    assert len(ARBITRATIONS) <= 2, "the float64 arbitration is meant for a rare host-side cdist inaccuracy"
 
 
 def test_topk_large_k_and_small_corpus():
@@ -201,8 +207,8 @@ def test_chunk_merge_and_evaluator_metrics_bit_identical():
             if got_ids != want_ids:      # only legal difference: swaps of scores tied within 1e-6
                 identical = False
                 want_val, want_idx = _oracle_topk(q, c, 10, fn, chunk=3000)
-                if fn == "cos_sim":
-                    assert_same_ranking(ranked[fn].indices, ranked[fn].values, want_idx, want_val, fn)
+                assert_same_ranking(ranked[fn].indices, ranked[fn].values, want_idx, want_val, fn,
+                                    scale=float(want_val.abs().max()) if fn == "dot_score" else 1.0)
             # metrics are bit-identical GIVEN the ranking: feed our ranking to the reference loops
             own_hits = [[{"corpus_id": f"d{j}", "score": float(-r)} for r, j in enumerate(row)] for row in got_rows]
             want_m = ref.compute_metrics(own_hits)
@@ -459,12 +465,8 @@ def test_candidate_exchange_emulated_on_one_gpu():
                                           master.inv_norm.data_ptr() if cos else None, master.stats.data_ptr(),
                                           vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), scratch.data_ptr(),
                                           _lib.stream_ptr(dev)))
-        if score == "dot_score":
-            scale = float(want_val.abs().max())
-            torch.testing.assert_close(vals.cpu() / scale, want_val / scale, rtol=0, atol=2e-6)
-            assert (idx.cpu() == want_idx).float().mean() > 0.999
-        else:
-            assert_same_ranking(idx, vals, want_idx, want_val, f"candidate exchange {score}")
+        scale = float(want_val.abs().max()) if score == "dot_score" else 1.0
+        assert_same_ranking(idx, vals, want_idx, want_val, f"candidate exchange {score}", scale=scale)
         assert bool((margin > 0).all()), score
 
 
@@ -549,3 +551,85 @@ def test_evaluator_scores_device_resident_corpus_in_one_pass():
     assert ev.compute_metrices(model) == ev.compute_metrices(model, corpus_embeddings=table[300:])
     host = ev.rank(model, corpus_embeddings=table[300:].cpu())          # host embeddings: chunked copies, same result
     assert all(torch.equal(host[fn].indices, chunked[fn].indices) for fn in chunked)
+
+
+def test_evaluator_csv_is_byte_identical_to_the_reference_writer(tmp_path):
+    """The PRODUCT's CSV writer, with the script defaults of ir_evauation_script.py:163-177 (k-lists up to
+    900, three score functions, write_csv=True): ``ev(model, output_path)`` called twice (header once, two
+    rows) must produce the same bytes as the oracle evaluator's file whenever the rankings are
+    identical, and the same header and row layout in any case."""
+    import os
+    import qst_b200
+    from oracle import ir_oracle
+    q, c, queries, corpus, relevant = qst_b200.synth.ir_eval_set(300, 4000, 96)
+    table = torch.cat([q, c])
+    kl = [1, 3, 5, 10, 20, 50, 100, 200, 500, 900]
+    kw = dict(mrr_at_k=kl, ndcg_at_k=kl, accuracy_at_k=kl, precision_recall_at_k=kl, map_at_k=kl, name="val")
+    ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
+        "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score}, **kw)
+    ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, score_functions={
+        "cos_sim": ir_oracle.cos_sim, "dot_score": ir_oracle.dot_score, "euclid_score": ir_oracle.euclidean_score}, **kw)
+    assert ev.write_csv and ev.csv_file == ref.csv_file
+    ours, theirs = tmp_path / "ours", tmp_path / "theirs"
+    ours.mkdir(); theirs.mkdir()
+    model, ref_model = qst_b200.synth.TableModel(table.to(_dev())), ir_oracle.PrecomputedEmbeddingModel(table)
+    got = [ev(model, output_path=str(ours), epoch=e, steps=s_) for e, s_ in ((0, 100), (1, -1))]
+    want = [ref(ref_model, output_path=str(theirs), epoch=e, steps=s_) for e, s_ in ((0, 100), (1, -1))]
+    a = open(os.path.join(ours, ev.csv_file), "rb").read()
+    b = open(os.path.join(theirs, ref.csv_file), "rb").read()
+    la, lb = a.decode().splitlines(), b.decode().splitlines()
+    assert len(la) == len(lb) == 3 and la[0] == lb[0], "one header, two rows, same columns in the same order"
+    assert [len(r.split(",")) for r in la] == [len(r.split(",")) for r in lb]
+    # identical rankings (the normal case on this data) -> identical bytes and identical return values
+    ranked = ev.rank(model)
+    hits = ref.collect_hits(ref_model)
+    same = all([[f"d{j}" for j in row] for row in ranked[fn].indices.cpu().tolist()] == ir_oracle.ranked_ids(hits[fn], 900)
+               for fn in ("cos_sim", "dot_score", "euclid_score"))
+    if same:
+        assert a == b
+        assert got == want
+    else:   # tie swaps: every cell still parses and agrees to 1e-12 (metrics move by a swap inside a tie only at k cut-offs)
+        print("rankings differ by tie swaps; CSV compared cell by cell")
+        for ra, rb in zip(la[1:], lb[1:]):
+            for x, y in zip(ra.split(","), rb.split(",")):
+                assert abs(float(x) - float(y)) <= 1e-3
+    assert all(v == 0 for v in ev.last_uncertified.values())
+
+
+def test_exact_rescan_serves_more_than_8192_flagged_queries():
+    """one pass of the re-scan lists at most 8192 flagged queries; the call must keep going
+    until every flagged query has been repaired (here: all 9000 of them, none certified beforehand)."""
+    import ctypes as C
+    from qst_b200 import _lib, scoring
+    lib = _lib.load()
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    Q, N, D, k = 9000, 1500, 32, 10
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, k, "dot_score")
+    qd, cd = q.to(dev).contiguous(), c.to(dev).contiguous()
+    vals = torch.full((Q, k), float("-inf"), device=dev)      # k-th best so far = -inf: every row qualifies
+    idx = torch.full((Q, k), -1, dtype=torch.int64, device=dev)
+    margin = torch.full((Q,), -1.0, device=dev)
+    scratch = torch.empty(lib.qst_exact_rescan_workspace_bytes(Q, k), dtype=torch.uint8, device=dev)
+    _lib.check(lib.qst_exact_rescan(Q, N, D, k, _lib.QST_SCORE_DOT, qd.data_ptr(), None, cd.data_ptr(), None, 0,
+                                    vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), scratch.data_ptr(),
+                                    _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert bool(torch.isinf(margin).all()) and bool((margin > 0).all()), int((~(margin > 0)).sum())
+    scale = float(want_val.abs().max())
+    assert_same_ranking(idx, vals, want_idx, want_val, "rescan of 9000 flagged queries", scale=scale)
+    # and rows wider than the old 3200-column limit of the re-scan are accepted (query batch in smem shrinks)
+    D2 = 4000
+    q2, c2 = torch.randn(3, D2, generator=g), torch.randn(200, D2, generator=g)
+    w2v, w2i = _oracle_topk(q2, c2, 5, "dot_score")
+    v2 = torch.full((3, 5), float("-inf"), device=dev)
+    i2 = torch.full((3, 5), -1, dtype=torch.int64, device=dev)
+    m2 = torch.full((3,), -1.0, device=dev)
+    s2 = torch.empty(lib.qst_exact_rescan_workspace_bytes(3, 5), dtype=torch.uint8, device=dev)
+    _lib.check(lib.qst_exact_rescan(3, 200, D2, 5, _lib.QST_SCORE_DOT, q2.to(dev).data_ptr(), None,
+                                    c2.to(dev).contiguous().data_ptr(), None, 0, v2.data_ptr(), i2.data_ptr(),
+                                    m2.data_ptr(), s2.data_ptr(), _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert_same_ranking(i2, v2, w2i, w2v, "rescan D=4000", scale=float(w2v.abs().max()))

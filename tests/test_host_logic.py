@@ -137,6 +137,10 @@ def test_ir_evaluation_set_loader_and_quadruplet_evaluator_construction(tmp_path
                "relevant": {"0": ["0", "2"], "1": ["5", "5"]}, "random_seed": 14}, open(path, "w"))
     queries, corpus, relevant = qst_b200.load_ir_evaluation_set(str(path))
     assert relevant == {"0": {"0", "2"}, "1": {"5"}} and list(corpus) == ["0", "2", "5"]
+    # the reference's literal reload (ir_evauation_script.py:94-96): every query's relevant set is the
+    # set of all query ids
+    _, _, rel_ref = qst_b200.load_ir_evaluation_set(str(path), reference_compatible=True)
+    assert rel_ref == {"0": {"0", "1"}, "1": {"0", "1"}}
     ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
         "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score})
     assert [sorted(p) for p in ev._relevant_positions] == [[0, 1], [2]]   # set order is hash-dependent
