@@ -243,17 +243,55 @@ def loss_config2(dev, peaks):
         us = a.elapsed_time(b) * 1e3 / (reps * sets)
         out[name] = {"us_per_step": us, "gbs_algorithmic": 8 * B * D * 4 / (us * 1e-6) / 1e9,
                      "kernel_launches_per_step": launches // sets}
-    # the Python API as a user calls it (autograd Function), wall time per fwd+bwd
+    # the Python API as a user calls it: forward + backward through autograd, gradients reset to None
+    # between steps as optimizer.zero_grad() does; wall time per step.  Next to it what torch's autograd
+    # engine costs for a custom Function that launches NOTHING (the floor of any drop-in loss module),
+    # the same step without autograd (loss_and_grads: one launch), and the reference's formulation
+    # (three F.triplet_margin_loss calls, models/losses/losses.py:35-69) on the same GPU.
+    import torch.nn.functional as F
     xs = [x.requires_grad_(True) for x in data[0]]
     mod = qst_b200.GammaQuadrupletLoss(gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5)
-    for _ in range(5):
-        mod(*xs).backward()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(50):
-        mod(*xs).backward()
-    torch.cuda.synchronize()
-    out["python_api_autograd_us_per_step"] = (time.perf_counter() - t0) / 50 * 1e6
+
+    class _Floor(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, a, p, q, n, buf, l0):
+            ctx.buf = buf
+            return l0
+
+        @staticmethod
+        def backward(ctx, go):
+            b = ctx.buf.unbind(0)
+            return b[0], b[1], b[2], b[3], None, None
+
+    fbuf, fl0 = torch.zeros(4, B, D, device=dev), torch.zeros((), device=dev)
+
+    def torch_ops():
+        a, p, q, n = xs
+        return (F.triplet_margin_loss(a, p, n, margin=1.0) + 0.6 * F.triplet_margin_loss(a, q, n, margin=0.5)
+                + 0.4 * F.triplet_margin_loss(a, p, q, margin=0.5))
+
+    def wall(fn, iters, backward=True):
+        for _ in range(10):
+            for x in xs:
+                x.grad = None
+            r = fn()
+            if backward:
+                r.backward()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            for x in xs:
+                x.grad = None
+            r = fn()
+            if backward:
+                r.backward()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters * 1e6
+
+    out["python_api_autograd_us_per_step"] = wall(lambda: mod(*xs), 200)
+    out["torch_autograd_floor_us_per_step"] = wall(lambda: _Floor.apply(*xs, fbuf, fl0), 200)
+    out["python_api_no_autograd_us_per_step"] = wall(lambda: mod.loss_and_grads(*xs)[0], 200, backward=False)
+    out["torch_ops_reference_formulation_us_per_step"] = wall(torch_ops, 50)
     hbm = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
     out["algorithmic_bytes"] = 8 * B * D * 4
     out["hbm_peak_gbs"] = hbm

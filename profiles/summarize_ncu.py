@@ -39,7 +39,10 @@ def main():
     rep, out = sys.argv[1], sys.argv[2]
     flop = float(sys.argv[3]) if len(sys.argv) > 3 else None
     nbytes = float(sys.argv[4]) if len(sys.argv) > 4 else None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):     # a raw page exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     launches = []

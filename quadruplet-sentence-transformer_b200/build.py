@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 
 SOURCES = ["common.cu", "quad_loss.cu", "quad_eval.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu",
            "comm.cu"]
-HEADERS = ["qst_common.cuh", "sm100_ptx.cuh"]
+HEADERS = ["qst_common.cuh", "sm100_ptx.cuh", "select_common.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -7,6 +7,8 @@
 // models/evaluators.py:572-588).  The fp32 rescoring makes the final order the one the
 // reference's fp32 cos_sim / dot_score produces (up to ties within 1e-6).
 #include "qst_common.cuh"
+#include "select_common.cuh"
+#include <stdlib.h>
 
 namespace qst {
 
@@ -728,6 +730,65 @@ __global__ void __launch_bounds__(kFinThreads) finalize_exact_kernel(int Q, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Candidate lists of the sharded path, ONE WARP per query row (qst_select_candidates for m <= 192).
+// A shard scores all G*q_own queries, so this kernel runs over G times more rows than anything on the
+// owner's side, each holding only a few dozen entries (S unit buffers of ~kunit entries): a CTA per row
+// spends its time on launch and barriers.  A warp gathers the row's unit buffers into a private
+// shared-memory window, keeps the m largest keys (exact radix select whenever the window fills up) and
+// writes the list + trailer (bound of everything not listed, count).  Entry order is arbitrary.
+// ------------------------------------------------------------------------------------------
+constexpr int kSelWarpWindow = 384;   // entries per warp window (m <= 192 leaves room to append between selects)
+constexpr int kSelWarps = 8;
+
+__global__ void __launch_bounds__(kSelWarps * 32) select_rows_warp_kernel(const FinParams P) {
+  __shared__ uint2 s_win[kSelWarps][kSelWarpWindow];
+  __shared__ int s_hist[kSelWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kSelWarps + warp;
+  if (q >= P.Q) return;
+  const int mt = q / P.rows_per_unit, r = q % P.rows_per_unit;
+  const int m = P.kprime;
+  uint2* win = s_win[warp];
+  int* hist = s_hist[warp];
+  int fill = 0;
+  bool reduced = false;
+  uint32_t T = 0u, Tstar = 0u;
+  for (int st = 0; st < P.stripes; ++st) {
+    const size_t urow = (size_t)(st * P.m_tiles + mt) * P.rows_per_unit + r;
+    const int cnt = P.unit_cnt[urow];
+    Tstar = max(Tstar, P.unit_thr[urow]);
+    const uint2* src = P.unit_cand + urow * (size_t)P.cap;
+    int pos = 0;
+    while (pos < cnt) {
+      if (fill == kSelWarpWindow) {
+        __syncwarp();
+        T = warp_select_compact(win, fill, m, hist, lane);
+        fill = m;
+        reduced = true;
+      }
+      const int take = min(kSelWarpWindow - fill, cnt - pos);
+      for (int i = lane; i < take; i += 32) win[fill + i] = src[pos + i];
+      fill += take;
+      pos += take;
+    }
+  }
+  __syncwarp();
+  if (fill > m) {
+    T = warp_select_compact(win, fill, m, hist, lane);
+    fill = m;
+    reduced = true;
+  }
+  __syncwarp();
+  uint2* dst = P.sel_out + (size_t)q * (m + 1);
+  for (int i = lane; i < m; i += 32) {
+    uint2 e = make_uint2(0u, 0xffffffffu);
+    if (i < fill) { e = win[i]; e.y = (uint32_t)((int64_t)(int32_t)e.y + P.idx_offset); }
+    dst[i] = e;
+  }
+  if (lane == 0) dst[m] = make_uint2(reduced ? max(T, Tstar) : Tstar, (uint32_t)fill);
+}
+
 __global__ void unpack_list_trailers_kernel(const uint2* __restrict__ lists, int64_t n, int m, uint32_t* thr, int* cnt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -796,6 +857,15 @@ extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* work
   P.unit_cand = reinterpret_cast<const uint2*>(ws + plan->off_cand);
   P.idx_offset = idx_offset;
   P.sel_out = reinterpret_cast<uint2*>(out_lists);
+  {
+    const char* e = getenv("QST_SELECT_CTA");   // 1 forces the CTA-per-row kernel (comparison / debugging)
+    if (m <= kSelWarpWindow / 2 && !(e && e[0] == '1')) {
+      select_rows_warp_kernel<<<(unsigned)ceil_div(plan->Q, kSelWarps), kSelWarps * 32, 0,
+                                reinterpret_cast<cudaStream_t>(stream)>>>(P);
+      QST_LAUNCH_CHECK();
+      return QST_OK;
+    }
+  }
   const size_t smem = (size_t)sm_cap * 8 + (size_t)m * 8 + 16;
   QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   finalize_kernel<<<(unsigned)plan->Q, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);

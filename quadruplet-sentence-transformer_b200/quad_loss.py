@@ -269,7 +269,12 @@ def gamma_quadruplet_loss_and_grads(x_anchor, x_pos, x_part, x_neg, gamma=DEFAUL
     _validate(gamma, margin_pos_neg, margin_pos_part, margin_part_neg, p, reduction)
     lib = _lib.load()
     prm = _params(gamma, margin_pos_neg, margin_pos_part, margin_part_neg, p, swap)
-    xs, shape, B, D, dt = _prepare(x_anchor.detach(), x_pos.detach(), x_part.detach(), x_neg.detach())
+    if isinstance(x_anchor, torch.Tensor) and _same_layout((x_anchor, x_pos, x_part, x_neg)):
+        xs, shape, dt = [x_anchor, x_pos, x_part, x_neg], x_anchor.shape, x_anchor.dtype   # nothing to convert
+        D = shape[-1]
+        B = x_anchor.numel() // D if D else 0
+    else:
+        xs, shape, B, D, dt = _prepare(x_anchor.detach(), x_pos.detach(), x_part.detach(), x_neg.detach())
     dev = xs[0].device
     red = _lib.REDUCTION_CODES[reduction]
     with torch.cuda.device(dev):

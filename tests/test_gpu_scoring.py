@@ -633,3 +633,43 @@ def test_exact_rescan_serves_more_than_8192_flagged_queries():
                                     m2.data_ptr(), s2.data_ptr(), _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert_same_ranking(i2, v2, w2i, w2v, "rescan D=4000", scale=float(w2v.abs().max()))
+
+
+@pytest.mark.parametrize("score", ["cos_sim", "dot_score", "euclid_score"])
+def test_script_default_max_k_on_config1_shape(score):
+    """max_k = 900 (ir_evauation_script.py:163-173) at BASELINE config 1's shape
+    (1000 x 10 000 x 384), every score function of `--score_functions all`, against the oracle."""
+    import qst_b200
+    g = torch.Generator().manual_seed(41)
+    q = torch.randn(1000, 384, generator=g)
+    c = torch.randn(10_000, 384, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, 900, score)
+    index = qst_b200.CorpusIndex(c.to(_dev()), score)
+    res = qst_b200.topk(q.to(_dev()), index, 900)
+    scale = float(want_val.abs().max()) if score == "dot_score" else 1.0
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, f"k=900 {score}", truth=(q, c, score), scale=scale)
+    assert bool((res.margin > 0).all())
+
+
+def test_max_k_900_on_a_long_corpus_sampled_against_brute_force():
+    """k = 900 where it costs something: 4000 queries x 300 000 corpus rows x 128.  Size-independent
+    properties for every query (certified, sorted, ids distinct and in range) and a brute-force fp32
+    comparison for a sample."""
+    import qst_b200
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(43)
+    Q, N, D, k = 4000, 300_000, 128, 900
+    q = torch.randn(Q, D, generator=g, device=dev)
+    c = torch.randn(N, D, generator=g, device=dev)
+    res = qst_b200.topk(q, qst_b200.CorpusIndex(c, "cos_sim"), k)
+    assert bool((res.margin > 0).all())
+    assert bool((res.values[:, 1:] <= res.values[:, :-1]).all())
+    assert int(res.indices.min()) >= 0 and int(res.indices.max()) < N
+    srt = torch.sort(res.indices, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    sel = torch.linspace(0, Q - 1, 64, device=dev).long()
+    sc = torch.nn.functional.normalize(q[sel], dim=1) @ torch.nn.functional.normalize(c, dim=1).T
+    bv, bi = torch.topk(sc, k, dim=1)
+    differ = res.indices[sel] != bi
+    assert bool((((res.values[sel] - bv).abs() <= 2e-6) | ~differ).all())
+    assert float((res.values[sel] - bv).abs().max()) <= 2e-6
