@@ -209,6 +209,10 @@ int qst_score_select_peers(const qst_topk_plan* plan, const void* q_bf16, const 
 int qst_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle64);
 int qst_peer_buffer_open(const unsigned char* handle64, void** dev_ptr);
 int qst_peer_buffer_clear(void* dev_ptr, size_t offset, size_t bytes, qst_stream_t stream);
+/* Copy-engine transfer into / out of a peer-mapped buffer (cudaMemcpyAsync, device to device): uses no SM,
+ * so it proceeds underneath the persistent K2.  The sharded path pushes the fp32 queries of a rank into
+ * every peer's gather buffer this way while K2 runs. */
+int qst_peer_copy(void* dst, const void* src, size_t bytes, qst_stream_t stream);
 int qst_peer_buffer_close(void* peer_ptr);
 int qst_peer_buffer_destroy(void* dev_ptr);
 

@@ -75,6 +75,7 @@ SIGNATURES = {
     "qst_peer_buffer_create": (_INT, [C.c_size_t, C.POINTER(_P), C.c_char_p]),
     "qst_peer_buffer_open": (_INT, [C.c_char_p, C.POINTER(_P)]),
     "qst_peer_buffer_clear": (_INT, [_P, C.c_size_t, C.c_size_t, _P]),
+    "qst_peer_copy": (_INT, [_P, _P, C.c_size_t, _P]),
     "qst_peer_buffer_close": (_INT, [_P]),
     "qst_peer_buffer_destroy": (_INT, [_P]),
     "qst_finalize_topk": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),

@@ -73,6 +73,14 @@ extern "C" int qst_peer_buffer_clear(void* dev_ptr, size_t offset, size_t bytes,
   return QST_OK;
 }
 
+// Device-to-device copy into (or out of) a peer-mapped buffer, executed by the COPY ENGINES: no SM is
+// involved, so it runs underneath a persistent kernel that occupies every SM (K2).
+extern "C" int qst_peer_copy(void* dst, const void* src, size_t bytes, qst_stream_t stream) {
+  QST_CHECK_ARG(dst && src, "peer_copy: null pointer");
+  QST_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return QST_OK;
+}
+
 extern "C" int qst_peer_buffer_close(void* peer_ptr) {
   if (peer_ptr) QST_CUDA(cudaIpcCloseMemHandle(peer_ptr));
   return QST_OK;

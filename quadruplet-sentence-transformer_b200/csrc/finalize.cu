@@ -649,6 +649,72 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_kernel(int m, in
   }
 }
 
+// Same work, ONE WARP per (owner, query) row with the query row held in registers (D <= 1024, D % 4 == 0):
+// a shard sees G * q_own rows with only ~k'/G requested entries each, so a CTA per row mostly pays for
+// staging the query in shared memory and for its barriers.  The per-row operation order is exactly
+// warp_dot_f32's (lane-strided float4 chunks, four fmaf per chunk in x, y, z, w order, xor-tree sum), so
+// the scores are bit-identical to the CTA kernel's and to K3's.
+constexpr int kRescoreRegChunks = 8;   // float4 chunks per lane: D <= 32 * 4 * 8 = 1024
+
+template <bool SQ>
+__global__ void __launch_bounds__(kFinThreads) rescore_requests_warp_kernel(int64_t rows, int m, int D, int score,
+                                                                            const int32_t* __restrict__ req,
+                                                                            const float* __restrict__ q_f32,
+                                                                            const float* __restrict__ q_inv,
+                                                                            const float* __restrict__ c_f32,
+                                                                            const float* __restrict__ c_inv,
+                                                                            float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
+  if (q >= rows) return;
+  const int n4 = D / 4;
+  float4 qa[kRescoreRegChunks];
+  const float4* q4 = reinterpret_cast<const float4*>(q_f32 + (size_t)q * D);
+#pragma unroll
+  for (int c = 0; c < kRescoreRegChunks; ++c) {
+    const int i = lane + 32 * c;
+    qa[c] = i < n4 ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
+  const int32_t* rq = req + (size_t)q * m;
+  float* o = out + (size_t)q * m;
+  for (int j0 = 0; j0 < m; j0 += 32) {
+    const int jj = j0 + lane;
+    const int my = jj < m ? rq[jj] : -1;
+    if (jj < m && my < 0) o[jj] = -INFINITY;
+    unsigned valid = __ballot_sync(0xffffffffu, my >= 0);
+    while (valid) {
+      // two requested rows per trip: twice the loads in flight
+      const int l0 = __ffs(valid) - 1;
+      valid &= valid - 1;
+      const int l1 = valid ? __ffs(valid) - 1 : -1;
+      if (l1 >= 0) valid &= valid - 1;
+      const int r0 = __shfl_sync(0xffffffffu, my, l0);
+      const int r1 = l1 >= 0 ? __shfl_sync(0xffffffffu, my, l1) : r0;
+      const float4* p0 = reinterpret_cast<const float4*>(c_f32 + (size_t)r0 * D);
+      const float4* p1 = reinterpret_cast<const float4*>(c_f32 + (size_t)r1 * D);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kRescoreRegChunks; ++c) {
+        const int i = lane + 32 * c;
+        if (i < n4) {
+          const float4 x = __ldg(p0 + i);
+          const float4 y = __ldg(p1 + i);
+          const float4 a = qa[c];
+          a0 = acc1<SQ>(a.x, x.x, a0); a0 = acc1<SQ>(a.y, x.y, a0); a0 = acc1<SQ>(a.z, x.z, a0); a0 = acc1<SQ>(a.w, x.w, a0);
+          a1 = acc1<SQ>(a.x, y.x, a1); a1 = acc1<SQ>(a.y, y.y, a1); a1 = acc1<SQ>(a.z, y.z, a1); a1 = acc1<SQ>(a.w, y.w, a1);
+        }
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      if (lane == 0) {
+        o[j0 + l0] = SQ ? a0 : apply_score(a0, score, qi, c_inv, r0);
+        if (l1 >= 0) o[j0 + l1] = SQ ? a1 : apply_score(a1, score, qi, c_inv, r1);
+      }
+    }
+  }
+}
+
 constexpr int kExactMax = 2048;   // entries one query can get back (k' <= 2048)
 
 __global__ void __launch_bounds__(kFinThreads) finalize_exact_kernel(int Q, int G, int m, int k, int score, int D, int64_t n_total,
@@ -949,6 +1015,20 @@ extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, c
                 (long long)rows, m, (long long)D);
   QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "rescore_requests: unknown score %d", score);
   QST_CHECK_ARG(score != QST_SCORE_COS || (q_inv && c_inv), "rescore_requests: cos score needs inverse norms");
+  {
+    const char* e = getenv("QST_RESCORE_CTA");   // 1 forces the CTA-per-row kernel (comparison / debugging)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(c_f32) | reinterpret_cast<uintptr_t>(q_f32)) & 15u) == 0;
+    if (D % 4 == 0 && D <= 128 * kRescoreRegChunks && aligned && !(e && e[0] == '1')) {
+      const unsigned grid = (unsigned)ceil_div(rows, kFinWarps);
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      if (score == QST_SCORE_EUCLID)
+        rescore_requests_warp_kernel<true><<<grid, kFinThreads, 0, st>>>(rows, m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+      else
+        rescore_requests_warp_kernel<false><<<grid, kFinThreads, 0, st>>>(rows, m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+      QST_LAUNCH_CHECK();
+      return QST_OK;
+    }
+  }
   const size_t smem = round_up((size_t)D * 4, 16);
   QST_CUDA(cudaFuncSetAttribute(rescore_requests_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rescore_requests_kernel<<<(unsigned)rows, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(

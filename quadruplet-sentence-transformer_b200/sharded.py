@@ -132,6 +132,54 @@ class PeerHints:
             self.buffers = None
 
 
+class PeerGather:
+    """All-gather of one fp32 block per rank through the COPY ENGINES into peer-mapped buffers.
+
+    The sharded-master path needs the fp32 queries of every rank on every rank -- but only after K2, for
+    the exact rescoring.  An NCCL all-gather would sit on the critical path in front of K2 (its kernel
+    cannot become resident beside the persistent K2); copy-engine transfers use no SM and run underneath
+    K2.  Every rank pushes its block into the gather buffer of every rank on a side stream; the consumer
+    kernel is ordered after (a) this rank's own pushes (event) and (b) a later collective of the same
+    step in which every rank takes part only after ITS pushes have completed (the all-to-all of the
+    candidate lists) -- so every block has landed.  Two generations alternate between steps: a rank can
+    be at most one step ahead of another (there are collectives in every step), so a fast rank never
+    writes into a buffer a slow rank is still reading."""
+
+    def __init__(self, block_bytes: int, comm: Comm, device: torch.device, own_stream: bool):
+        self.block_bytes, self.comm, self.device = block_bytes, comm, device
+        self.gen_bytes = ((block_bytes * comm.world + 255) // 256) * 256
+        self.buffers = comm.shared_buffers(2 * self.gen_bytes, device)
+        self.ok = self.buffers is not None
+        self.side = torch.cuda.Stream(device=device) if (self.ok and own_stream) else None
+        self.step = 0
+
+    def push(self, block: torch.Tensor):
+        """Start pushing `block` (this rank's contiguous fp32 block) to every rank; returns
+        (pointer of this rank's gathered buffer for this step, event to wait for before the collective
+        that publishes the pushes)."""
+        lib = _lib.load()
+        off = (self.step % 2) * self.gen_bytes
+        self.step += 1
+        main = torch.cuda.current_stream(self.device)
+        st = self.side if self.side is not None else main
+        if st is not main:
+            st.wait_stream(main)                       # the block has been produced on the main stream
+        dst_off = off + self.comm.rank * self.block_bytes
+        with torch.cuda.stream(st):
+            for base in [self.buffers.local] + list(self.buffers.peers):
+                _lib.check(lib.qst_peer_copy(C.c_void_p(base + dst_off), block.data_ptr(), self.block_bytes,
+                                             st.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(st)
+        block.record_stream(st)
+        return self.buffers.local + off, ev
+
+    def close(self):
+        if self.buffers is not None:
+            self.buffers.close()
+            self.buffers = None
+
+
 class ShardedCorpus:
     """This rank's shard of an N-row corpus + the collective top-k over all shards.
 
@@ -157,6 +205,8 @@ class ShardedCorpus:
         self._side = torch.cuda.Stream(device=self.index.device) if self.world > 1 else None
         self._peer_hints: Optional[PeerHints] = None
         self._peer_hints_off = bool(os.environ.get("QST_NO_PEER_HINTS"))
+        self._peer_gather: Optional[PeerGather] = None
+        self._peer_gather_off = bool(os.environ.get("QST_NO_PEER_GATHER"))
         self._timing = [] if os.environ.get("QST_SHARD_TIMING") else None   # debug: per-stage CUDA events
         self.master = None
         self.last_rescanned = 0      # queries repaired by the distributed exact re-scan in the last call
@@ -223,6 +273,22 @@ class ShardedCorpus:
                 self._peer_hints_off = True       # no peer-writable memory here: per-shard thresholds only
                 return None
         return self._peer_hints
+
+    def _gather_for(self, block_bytes: int, dev) -> Optional[PeerGather]:
+        """Copy-engine gather buffers for blocks of `block_bytes` (collective on first use / resize)."""
+        if self._peer_gather_off or self.world == 1:
+            return None
+        if self._peer_gather is None or self._peer_gather.block_bytes != block_bytes:
+            if self._peer_gather is not None:
+                torch.cuda.synchronize(dev)
+                self.comm.barrier()
+                self._peer_gather.close()
+            from .comm import LocalComm
+            self._peer_gather = PeerGather(block_bytes, self.comm, dev, own_stream=not isinstance(self.comm, LocalComm))
+            if not self._peer_gather.ok:
+                self._peer_gather_off = True
+                return None
+        return self._peer_gather
 
     def _mark(self, marks, name):
         if marks is not None:
@@ -320,17 +386,36 @@ class ShardedCorpus:
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             self._mark(marks, "start")
-            # every rank rescoring rows of ITS shard needs the fp32 queries of all ranks: one
-            # all-gather; K1 then runs on all of them locally (the bf16 operands are not sent)
-            q_all = own_queries.float().contiguous()
-            if G > 1:
-                q_all = comm.all_gather(q_all)
-            pq = scoring.prepare_rows(q_all, scoring.QUERY_PREP[score])
+            # Every rank rescoring rows of ITS shard needs the fp32 queries of all ranks -- but only
+            # AFTER K2.  With peer-mapped buffers they are pushed by the copy engines underneath K2 and
+            # only the bf16 operands (+ inverse norms) are all-gathered in front of it; without, the fp32
+            # queries are all-gathered and K1 runs on all of them locally.
+            own_f32 = own_queries.float().contiguous()
+            gather = self._gather_for(q_own * D * 4, dev) if G > 1 else None
+            if gather is not None:
+                pq_own = scoring.prepare_rows(own_f32, scoring.QUERY_PREP[score])
+                q_bf16 = comm.all_gather(pq_own.bf16)
+                q_inv_all = comm.all_gather(pq_own.inv_norm) if cos else None
+                # pushed AFTER the all-gathers are queued (the side stream waits for them): the pushes then
+                # share NVLink with nothing and run entirely underneath K2
+                q_all_ptr, pushed = gather.push(pq_own.f32)
+                own_f32_ptr, own_err_ptr = pq_own.f32.data_ptr(), pq_own.err.data_ptr()
+                keep = (pq_own, q_bf16, q_inv_all)
+            else:
+                q_all = comm.all_gather(own_f32) if G > 1 else own_f32
+                pq = scoring.prepare_rows(q_all, scoring.QUERY_PREP[score])
+                own = slice(r * q_own, (r + 1) * q_own)
+                q_all_ptr, pushed, q_bf16, q_inv_all = pq.f32.data_ptr(), None, pq.bf16, (pq.inv_norm if cos else None)
+                own_f32_ptr, own_err_ptr = pq.f32[own].data_ptr(), pq.err[own].data_ptr()
+                keep = (pq,)
             self._mark(marks, "gather_q+prep")
-            lists, m, kprime_all = self._select_pass(pq.bf16, q_pad, k, kprime, marks)
+            lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks)
+            if pushed is not None:
+                # this rank's pushes are done before it enters the exchange; the exchange completes only
+                # after every rank has entered it, i.e. after every rank's pushes are done
+                torch.cuda.current_stream(dev).wait_event(pushed)
             recv = comm.all_to_all(lists) if G > 1 else lists                     # [G, q_own, m+1, 2]
             self._mark(marks, "all_to_all")
-            own = slice(r * q_own, (r + 1) * q_own)
             req = torch.empty((G * q_own, m), dtype=torch.int32, device=dev)      # [G shards, q_own, m]
             bound = torch.empty(q_own, dtype=torch.int32, device=dev)
             scratch = self._ws(lib.qst_finalize_lists_scratch_bytes(q_own, G), "lists")
@@ -340,8 +425,8 @@ class ShardedCorpus:
             req_in = comm.all_to_all(req) if G > 1 else req                       # [G owners, q_own, m]
             exact_out = torch.empty((G * q_own, m), dtype=torch.float32, device=dev)
             c = self.index.rows
-            _lib.check(lib.qst_rescore_requests(G * q_own, m, D, code, req_in.data_ptr(), pq.f32.data_ptr(),
-                                                pq.inv_norm.data_ptr() if cos else None, c.f32.data_ptr(),
+            _lib.check(lib.qst_rescore_requests(G * q_own, m, D, code, req_in.data_ptr(), q_all_ptr,
+                                                _lib.ptr(q_inv_all), c.f32.data_ptr(),
                                                 c.inv_norm.data_ptr() if cos else None, exact_out.data_ptr(), st))
             self._mark(marks, "rescore")
             exact_in = comm.all_to_all(exact_out) if G > 1 else exact_out         # [G shards, q_own, m]
@@ -349,18 +434,19 @@ class ShardedCorpus:
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
             margin = torch.empty(q_own, dtype=torch.float32, device=dev)
             _lib.check(lib.qst_finalize_exact(q_own, G, m, k, code, D, self.n_total, req.data_ptr(),
-                                              exact_in.data_ptr(), bound.data_ptr(), pq.f32[own].data_ptr(),
-                                              pq.err[own].data_ptr(), self.global_stats.data_ptr(),
+                                              exact_in.data_ptr(), bound.data_ptr(), own_f32_ptr,
+                                              own_err_ptr, self.global_stats.data_ptr(),
                                               vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), st))
             self._mark(marks, "replies+finalize")
             if exact:
-                self._distributed_rescan(pq, q_own, k, vals, idx, margin)
+                self._distributed_rescan(q_all_ptr, q_inv_all, q_own, k, vals, idx, margin)
+            del keep
             self._mark(marks, "rescan")
             if marks is not None:
                 self._timing.append(marks)
         return vals, idx, margin
 
-    def _distributed_rescan(self, pq, q_own, k, vals, idx, margin):
+    def _distributed_rescan(self, q_all_ptr, q_inv_all, q_own, k, vals, idx, margin):
         """Backstop of the sharded-master path: queries whose certificate failed are re-scanned in fp32
         by EVERY shard against its own rows (``qst_exact_rescan_lists``: rows scoring at least the
         owner's current k-th exact score), the G lists go back to the owner and are merged.  Needs one
@@ -389,8 +475,8 @@ class ShardedCorpus:
         for lo in range(0, n_flagged, 8192):                                           # one pass serves 8192 queries
             sel = flagged & (rank_of >= lo) & (rank_of < lo + 8192)
             m_in = torch.where(sel, torch.full_like(kth, -1.0), torch.ones_like(kth))
-            _lib.check(lib.qst_exact_rescan_lists(n_rows, self.index.n, self.index.d, k, code, pq.f32.data_ptr(),
-                                                  pq.inv_norm.data_ptr() if cos else None, c.f32.data_ptr(),
+            _lib.check(lib.qst_exact_rescan_lists(n_rows, self.index.n, self.index.d, k, code, q_all_ptr,
+                                                  _lib.ptr(q_inv_all) if cos else None, c.f32.data_ptr(),
                                                   c.inv_norm.data_ptr() if cos else None, self.start, kth.data_ptr(),
                                                   m_in.data_ptr(), lists_v.data_ptr(), lists_i.data_ptr(),
                                                   overflow.data_ptr(), scratch.data_ptr(), st))
