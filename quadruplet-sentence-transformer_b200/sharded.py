@@ -210,6 +210,7 @@ class ShardedCorpus:
         self._timing = [] if os.environ.get("QST_SHARD_TIMING") else None   # debug: per-stage CUDA events
         self.master = None
         self.last_rescanned = 0      # queries repaired by the distributed exact re-scan in the last call
+        self._pending = None         # deferred certificate check of the last call (exact="deferred")
         if full_master is not None:
             if full_master.shape[0] != n_total:
                 raise ValueError(f"full_master must have {n_total} rows, got {full_master.shape[0]}")
@@ -331,7 +332,16 @@ class ShardedCorpus:
           rank is the same q*k' rows as on one GPU.
         * replicated master: the owner rescoring-finalises the lists itself from its copy of the whole
           fp32 corpus (``qst_finalize_lists``); only bf16 query operands travel.
+
+        ``exact=True``: queries whose certificate failed are re-scanned exactly before the call returns;
+        with a sharded master that costs ONE host read per call ("is anything flagged, anywhere?").
+        ``exact="deferred"`` (sharded master) moves that read to the next ``topk_owned`` call or to
+        ``finish_exact()``, whichever comes first -- by then the flag has long arrived, nothing stalls --
+        and patches the returned tensors in place in the rare case a re-scan is needed.  A stream of
+        batches should use it and call ``finish_exact()`` after the last one.
         """
+        if exact == "deferred" and (self.master is not None or self.world == 1):
+            exact = True        # the replicated-master / single-GPU re-scans are device-driven: nothing to defer
         if self.master is not None:
             return self._topk_owned_replicated(own_queries, k, kprime, exact)
         return self._topk_owned_sharded(own_queries, k, kprime, exact)
@@ -375,6 +385,7 @@ class ShardedCorpus:
         lib = _lib.load()
         dev = self.index.device
         comm, G, r = self.comm, self.world, self.rank
+        self.finish_exact()                 # the previous call's deferred certificate check, if any
         own_queries = own_queries.to(dev)
         q_own = own_queries.shape[0]
         q_pad = q_own * G
@@ -438,7 +449,16 @@ class ShardedCorpus:
                                               own_err_ptr, self.global_stats.data_ptr(),
                                               vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), st))
             self._mark(marks, "replies+finalize")
-            if exact:
+            if exact == "deferred":
+                # decide about the re-scan one call later (or in finish_exact()): nothing stalls here
+                state = torch.stack([margin, vals[:, k - 1]], dim=1).contiguous()
+                all_state = comm.all_gather(state) if G > 1 else state
+                flag = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+                flag.copy_((~(all_state[:, 0] > 0)).any().to(torch.int32).view(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pending = (ev, flag, all_state, q_all_ptr, q_inv_all, q_own, k, vals, idx, margin, keep)
+            elif exact:
                 self._distributed_rescan(q_all_ptr, q_inv_all, q_own, k, vals, idx, margin)
             del keep
             self._mark(marks, "rescan")
@@ -446,7 +466,24 @@ class ShardedCorpus:
                 self._timing.append(marks)
         return vals, idx, margin
 
-    def _distributed_rescan(self, q_all_ptr, q_inv_all, q_own, k, vals, idx, margin):
+    def finish_exact(self) -> int:
+        """Completes a call made with ``exact="deferred"``: waits for that call's certificate flag (long
+        since on the host when this runs one call later) and, if any query anywhere was left uncertified,
+        runs the distributed exact re-scan and patches that call's result tensors IN PLACE.  Collective
+        (every rank sees the same flag).  Returns the number of queries that were re-scanned."""
+        pend, self._pending = getattr(self, "_pending", None), None
+        if pend is None:
+            return 0
+        ev, flag, all_state, q_all_ptr, q_inv_all, q_own, k, vals, idx, margin, keep = pend
+        ev.synchronize()
+        if int(flag[0]) == 0:
+            self.last_rescanned = 0
+            return 0
+        with torch.cuda.device(self.index.device):
+            self._distributed_rescan(q_all_ptr, q_inv_all, q_own, k, vals, idx, margin, all_state=all_state)
+        return self.last_rescanned
+
+    def _distributed_rescan(self, q_all_ptr, q_inv_all, q_own, k, vals, idx, margin, all_state=None):
         """Backstop of the sharded-master path: queries whose certificate failed are re-scanned in fp32
         by EVERY shard against its own rows (``qst_exact_rescan_lists``: rows scoring at least the
         owner's current k-th exact score), the G lists go back to the owner and are merged.  Needs one
@@ -457,8 +494,9 @@ class ShardedCorpus:
         cos = self.score == "cos_sim"
         code = scoring.SCORE_CODES[self.score]
         st = _lib.stream_ptr(dev)
-        state = torch.stack([margin, vals[:, k - 1]], dim=1).contiguous()             # [q_own, 2]
-        all_state = comm.all_gather(state) if G > 1 else state                         # [G*q_own, 2]
+        if all_state is None:
+            state = torch.stack([margin, vals[:, k - 1]], dim=1).contiguous()         # [q_own, 2]
+            all_state = comm.all_gather(state) if G > 1 else state                     # [G*q_own, 2]
         flagged = ~(all_state[:, 0] > 0)
         n_flagged = int(flagged.sum())                                                 # host sync, same on all ranks
         self.last_rescanned = n_flagged

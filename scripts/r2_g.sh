@@ -1,5 +1,6 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_sharded_emulated.py -x -q > gpurun_out/r2_g_tests.txt 2>&1
-tail -30 gpurun_out/r2_g_tests.txt
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_g_tests.txt 2>&1
+tail -6 gpurun_out/r2_g_tests.txt
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.txt 2>&1; tail -2 gpurun_out/r2_smoke.txt

@@ -103,3 +103,42 @@ def test_sharded_near_ties_go_through_the_exact_rescan(master):
         assert bool((m > 0).all())
     if master == "sharded":
         assert out[0][3] > 0, "this data is meant to fail certificates and exercise the distributed re-scan"
+
+
+def test_deferred_certificate_check_patches_results_in_place():
+    """``exact="deferred"``: the call returns without a host read; the next call (or ``finish_exact``)
+    re-scans what was left uncertified and patches the tensors of the earlier call in place."""
+    import qst_b200
+    from qst_b200 import comm, sharded
+    g = torch.Generator().manual_seed(3)
+    Q, N, D, k, G = 40, 6000, 64, 10, 2
+    cent = torch.randn(30, D, generator=g)
+    c = cent[torch.randint(0, 30, (N,), generator=g)] + 1e-4 * torch.randn(N, D, generator=g)
+    q = cent[torch.randint(0, 30, (Q,), generator=g)] + 1e-3 * torch.randn(Q, D, generator=g)
+    want_val, want_idx = _oracle_topk(q, c, k, "cos_sim")
+    dev = _dev()
+    q_dev, c_dev = q.to(dev), c.to(dev)
+    q_own = Q // G
+
+    def body(cm):
+        s, e = sharded.shard_bounds(N, cm.world, cm.rank)
+        corp = sharded.ShardedCorpus(c_dev[s:e], N, "cos_sim", comm=cm)
+        own = q_dev[cm.rank * q_own:(cm.rank + 1) * q_own]
+        v1, i1, m1 = corp.topk_owned(own, k, exact="deferred")
+        torch.cuda.synchronize()
+        flagged_before = int((~(m1 > 0)).sum())
+        v2, i2, m2 = corp.topk_owned(own, k, exact="deferred")      # checks + repairs the first call
+        torch.cuda.synchronize()
+        first_ok = bool((m1 > 0).all())
+        n2 = corp.finish_exact()                                    # ... and this one the second
+        torch.cuda.synchronize()
+        return v1.cpu(), i1.cpu(), m1.cpu(), v2.cpu(), i2.cpu(), m2.cpu(), flagged_before, first_ok, n2
+
+    out = comm.run_local_world(G, body)
+    assert sum(o[6] for o in out) > 0, "the data is meant to leave queries uncertified after the first pass"
+    for rank, (v1, i1, m1, v2, i2, m2, _, first_ok, n2) in enumerate(out):
+        lo, hi = rank * q_own, (rank + 1) * q_own
+        assert first_ok and n2 > 0
+        for v, i, m in ((v1, i1, m1), (v2, i2, m2)):
+            assert_same_ranking(i, v, want_idx[lo:hi], want_val[lo:hi], f"deferred rank {rank}")
+            assert bool((m > 0).all())
