@@ -216,6 +216,15 @@ int qst_peer_copy(void* dst, const void* src, size_t bytes, qst_stream_t stream)
 int qst_peer_buffer_close(void* peer_ptr);
 int qst_peer_buffer_destroy(void* dev_ptr);
 
+/* Dense exact score matrix out[Q, N] fp32 with K3's arithmetic (fp32 dot products on CUDA cores): what
+ * sentence_transformers.util.cos_sim / dot_score and the reference's euclidean_score
+ * (models/evaluators.py:392-405) return when called directly, e.g. at
+ * dataset/positive_examples_selection.py:55 and dataset/quadruplet_dataset.py:229-234.  For small inputs;
+ * retrieval-sized inputs go through qst_score_select / qst_finalize_topk and never build the matrix.
+ * q_inv / c_inv: inverse norms from qst_prep_rows (cos_sim) or NULL.  Q <= 65535 per call. */
+int qst_dense_scores(int64_t Q, int64_t N, int64_t D, int score, const float* q_f32, const float* q_inv,
+                     const float* c_f32, const float* c_inv, float* out, qst_stream_t stream);
+
 /* Debug/validation aid: raw tensor-core scores of one call written densely, out[Q, N] fp32.
  * Same kernel, same tiles, epilogue stores instead of selecting.  Small shapes only. */
 int qst_score_dense(const void* q_bf16, int64_t Q, const void* c_bf16, int64_t N, int64_t D_pad,

@@ -70,6 +70,7 @@ SIGNATURES = {
     "qst_topk_plan_set_kunit": (_INT, [C.POINTER(TopkPlan), _INT]),
     "qst_score_select": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P]),
     "qst_score_dense": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
+    "qst_dense_scores": (_INT, [_I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "qst_debug_read_trace": (_INT, [_P, _P, _P, _INT]),
     "qst_score_select_peers": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, C.POINTER(_P), _INT, _P]),
     "qst_peer_buffer_create": (_INT, [C.c_size_t, C.POINTER(_P), C.c_char_p]),

@@ -715,6 +715,32 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_warp_kernel(int6
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Dense exact scores [Q, N] in fp32 on CUDA cores, with the arithmetic of K3 (warp_dot_f32 +
+// apply_score): the direct-call form of cos_sim / dot_score / euclidean_score
+// (/root/reference/dataset/positive_examples_selection.py:55, dataset/quadruplet_dataset.py:229-234,
+// training/main.py:57 call them on small inputs and want the matrix).  Not a hot path: retrieval-sized
+// inputs go through K2/K3 and never materialise the matrix.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFinThreads) dense_scores_kernel(int64_t N, int D, int score, const float* __restrict__ q_f32,
+                                                                   const float* __restrict__ q_inv,
+                                                                   const float* __restrict__ c_f32,
+                                                                   const float* __restrict__ c_inv, float* __restrict__ out) {
+  extern __shared__ float dq_row[];
+  const int64_t q = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < D; i += kFinThreads) dq_row[i] = q_f32[(size_t)q * D + i];
+  __syncthreads();
+  const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
+  const bool vec4 = (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(c_f32) & 15u) == 0);
+  const bool sq = score == QST_SCORE_EUCLID;
+  for (int64_t row = (int64_t)blockIdx.x * kFinWarps + warp; row < N; row += (int64_t)gridDim.x * kFinWarps) {
+    const float* crow = c_f32 + (size_t)row * D;
+    const float d = sq ? warp_dot_f32<true>(dq_row, crow, D, vec4, lane) : warp_dot_f32<false>(dq_row, crow, D, vec4, lane);
+    if (lane == 0) out[(size_t)q * N + row] = apply_score(d, score, qi, c_inv, (int)row);
+  }
+}
+
 constexpr int kExactMax = 2048;   // entries one query can get back (k' <= 2048)
 
 __global__ void __launch_bounds__(kFinThreads) finalize_exact_kernel(int Q, int G, int m, int k, int score, int D, int64_t n_total,
@@ -1033,6 +1059,23 @@ extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, c
   QST_CUDA(cudaFuncSetAttribute(rescore_requests_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rescore_requests_kernel<<<(unsigned)rows, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
+
+extern "C" int qst_dense_scores(int64_t Q, int64_t N, int64_t D, int score, const float* q_f32, const float* q_inv,
+                                const float* c_f32, const float* c_inv, float* out, qst_stream_t stream) {
+  QST_CHECK_ARG(q_f32 && c_f32 && out, "dense_scores: null argument");
+  QST_CHECK_ARG(Q >= 1 && N >= 1 && D >= 1 && Q <= 65535 && N < (1ll << 31) && D * 4 <= 200 * 1024,
+                "dense_scores: bad shape Q=%lld N=%lld D=%lld (Q <= 65535 per call)", (long long)Q, (long long)N, (long long)D);
+  QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "dense_scores: unknown score %d", score);
+  QST_CHECK_ARG(score != QST_SCORE_COS || (q_inv && c_inv), "dense_scores: cos score needs inverse norms");
+  const size_t smem = round_up((size_t)D * 4, 16);
+  QST_CUDA(cudaFuncSetAttribute(dense_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t gx = ceil_div(N, kFinWarps);
+  if (gx > 1024) gx = 1024;
+  dense_scores_kernel<<<dim3((unsigned)gx, (unsigned)Q), kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      N, (int)D, score, q_f32, q_inv, c_f32, c_inv, out);
   QST_LAUNCH_CHECK();
   return QST_OK;
 }

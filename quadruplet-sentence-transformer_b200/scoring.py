@@ -245,19 +245,30 @@ def dense_tensorcore_scores(q_bf16: torch.Tensor, c_bf16: torch.Tensor) -> torch
 
 
 def _dense_scores(a, b, score: str) -> torch.Tensor:
-    """Dense fp32 [Q, N] scores through the exact path: top-N of every query, scattered back.
-
-    Only meant for the small direct uses of ``cos_sim`` in the reference (e.g.
-    ``dataset/positive_examples_selection.py:55``); N is limited to 1024 columns.
-    """
+    """Dense fp32 [Q, N] scores with K3's exact arithmetic (``qst_dense_scores``: fp32 dot products on
+    CUDA cores, bit-identical to the scores ``topk`` reports).  This is what the score functions return
+    when they are called directly, as the reference does on small inputs
+    (``dataset/positive_examples_selection.py:55``, ``dataset/quadruplet_dataset.py:229-234``,
+    ``training/main.py:57``); the evaluator never comes here."""
+    lib = _lib.load()
     a, b = _as_2d_cuda(a), _as_2d_cuda(b)
-    N = b.shape[0]
-    if N > 1024:
-        raise ValueError("dense score matrices are limited to 1024 corpus rows; use topk()/the evaluator "
-                         "for retrieval-sized inputs (the [Q, N] matrix is never materialised there)")
-    res = topk(a, CorpusIndex(b, score), k=N, kprime=max(32, ((N + 31) // 32) * 32), exact=False)
-    out = torch.empty((a.shape[0], N), dtype=torch.float32, device=a.device)
-    out.scatter_(1, res.indices.clamp_min(0), res.values)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError(f"embedding dims differ: {a.shape[1]} vs {b.shape[1]}")
+    dev = a.device
+    cos = score == "cos_sim"
+    pa = prepare_rows(a, _lib.QST_PREP_COS if cos else _lib.QST_PREP_RAW, want_bf16=False)
+    pb = prepare_rows(b.to(dev), _lib.QST_PREP_COS if cos else _lib.QST_PREP_RAW, want_bf16=False)
+    Q, N, D = pa.n, pb.n, pa.d
+    out = torch.empty((Q, N), dtype=torch.float32, device=dev)
+    if Q == 0 or N == 0:
+        return out
+    with torch.cuda.device(dev):
+        for s0 in range(0, Q, 65535):
+            s1 = min(Q, s0 + 65535)
+            _lib.check(lib.qst_dense_scores(s1 - s0, N, D, SCORE_CODES[score], pa.f32[s0:s1].data_ptr(),
+                                            pa.inv_norm[s0:s1].data_ptr() if cos else None, pb.f32.data_ptr(),
+                                            pb.inv_norm.data_ptr() if cos else None, out[s0:s1].data_ptr(),
+                                            _lib.stream_ptr(dev)))
     return out
 
 

@@ -673,3 +673,31 @@ def test_max_k_900_on_a_long_corpus_sampled_against_brute_force():
     differ = res.indices[sel] != bi
     assert bool((((res.values[sel] - bv).abs() <= 2e-6) | ~differ).all())
     assert float((res.values[sel] - bv).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("score", ["cos_sim", "dot_score", "euclid_score"])
+def test_score_functions_called_directly_return_the_dense_matrix(score):
+    """cos_sim / dot_score / euclidean_score called directly (the reference does at
+    dataset/positive_examples_selection.py:55 and dataset/quadruplet_dataset.py:229-234) return the fp32
+    [Q, N] matrix -- any N (round 1 stopped at 1024 columns) -- with the values top-k reports."""
+    import qst_b200
+    from oracle import ir_oracle
+    fn = {"cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score}[score]
+    ref = {"cos_sim": ir_oracle.cos_sim, "dot_score": ir_oracle.dot_score, "euclid_score": ir_oracle.euclidean_score}[score]
+    g = torch.Generator().manual_seed(12)
+    q = torch.randn(37, 96, generator=g)
+    c = torch.randn(3001, 96, generator=g) * (1 + torch.rand(3001, 1, generator=g))
+    got = fn(q.to(_dev()), c.to(_dev()))
+    want = ref(q, c)
+    scale = float(want.abs().max()) if score == "dot_score" else 1.0
+    assert got.shape == (37, 3001)
+    torch.testing.assert_close(got.cpu() / scale, want / scale, rtol=0, atol=1.2e-5 if score == "euclid_score" else 2e-6)
+    # 1-D inputs are promoted like the reference does, and the values are the ones topk() emits
+    one = fn(q[0].to(_dev()), c.to(_dev()))
+    assert one.shape == (1, 3001) and torch.equal(one[0], got[0])
+    res = qst_b200.topk(q.to(_dev()), qst_b200.CorpusIndex(c.to(_dev()), score), 10)
+    assert torch.equal(res.values, torch.gather(got, 1, res.indices))
+    # the negative-mining filter built on it (dataset/quadruplet_dataset.py:229-234)
+    if score == "cos_sim":
+        mask, scores = qst_b200.dissimilar_mask(q[0].to(_dev()), c.to(_dev()), 0.2)
+        assert mask.shape == (3001,) and torch.equal(mask, scores <= 0.2)
