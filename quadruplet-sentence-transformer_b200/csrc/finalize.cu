@@ -823,14 +823,14 @@ __global__ void __launch_bounds__(kFinThreads) finalize_exact_kernel(int Q, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// Candidate lists of the sharded path, ONE WARP per query row (qst_select_candidates for m <= 192).
+// Candidate lists of the sharded path, ONE WARP per query row (qst_select_candidates for m <= 256).
 // A shard scores all G*q_own queries, so this kernel runs over G times more rows than anything on the
 // owner's side, each holding only a few dozen entries (S unit buffers of ~kunit entries): a CTA per row
 // spends its time on launch and barriers.  A warp gathers the row's unit buffers into a private
 // shared-memory window, keeps the m largest keys (exact radix select whenever the window fills up) and
 // writes the list + trailer (bound of everything not listed, count).  Entry order is arbitrary.
 // ------------------------------------------------------------------------------------------
-constexpr int kSelWarpWindow = 384;   // entries per warp window (m <= 192 leaves room to append between selects)
+constexpr int kSelWarpWindow = 512;   // entries per warp window (m <= 256 leaves room to append between selects)
 constexpr int kSelWarps = 8;
 
 __global__ void __launch_bounds__(kSelWarps * 32) select_rows_warp_kernel(const FinParams P) {

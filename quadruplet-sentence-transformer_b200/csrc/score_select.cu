@@ -326,6 +326,9 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], int col0, cons
   // The stores are 8 bytes per lane to 32 different buffers -- uncoalesced but few, and far cheaper
   // in instructions than serving the rows cooperatively (the epilogue is issue-bound: one warp per
   // scheduler).
+  // (A group-wise build -- only look at a group of four columns when some lane's group maximum beats its
+  // threshold -- executes fewer instructions but was 5 % SLOWER: eight votes and branches per chunk cost
+  // more than 32 predicated compare + select pairs.  profiles/r02_k2_ab_grouped_mask.txt)
   unsigned above = 0u;
 #pragma unroll
   for (int j = 0; j < 32; ++j) above |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
