@@ -367,15 +367,42 @@ def parity_sample(comm, own_queries, vals, idx, rows_f32, start, k, n_sample=PAR
     bv, o = torch.topk(gv, k, dim=1)
     bi = torch.gather(gi, 1, o)
     differ = ours_i != bi
-    # where ids differ it must be a swap between scores that agree within float rounding (the two
-    # implementations sum in different orders): the VALUES at those positions still line up
-    ok_pos = ((ours_v - bv).abs() <= 2e-6) | ~differ
-    identical = int((~differ).all(dim=1).sum())
-    up_to_ties = int(ok_pos.all(dim=1).sum())
     n = G * per
+    identical = int((~differ).all(dim=1).sum())
+    # Scores we REPORT must agree with the reference's at every rank (same document or a tie partner);
+    # 5e-6: two fp32 summation orders of a 768-term dot product (observed: up to 9e-7 at |score| ~ 1).
+    value_bad = (ours_v - bv).abs() > 5e-6
+    ok_pos = ~differ
+    settled = 0
+    if bool(differ.any()):
+        # A different document at a rank is legal only as a swap inside a tie.  Neither side's fp32 value is
+        # trusted for that: both documents are scored in float64 by the rank that holds them, and the swap
+        # counts as a tie when the two exact scores agree within 2e-6 (fp32 rounding of a 768-term dot
+        # product, the reason two fp32 implementations may order such a pair differently).
+        bad_q, bad_j = differ.nonzero(as_tuple=True)
+        qd = torch.nn.functional.normalize(q_s[bad_q].double(), p=2, dim=1)
+
+        def exact64(ids):
+            loc = ids - start
+            mine = (loc >= 0) & (loc < rows_f32.shape[0])
+            sc = torch.full((ids.numel(),), float("-inf"), dtype=torch.float64, device=ids.device)
+            if bool(mine.any()):
+                rows = torch.nn.functional.normalize(rows_f32[loc[mine]].double(), p=2, dim=1)
+                sc[mine] = (qd[mine] * rows).sum(1)
+            # every other rank holds -inf for this row: the max over ranks is the owner's value
+            return comm.all_reduce_max(sc.float()).double() if G > 1 else sc
+
+        s_ours, s_ref = exact64(ours_i[bad_q, bad_j]), exact64(bi[bad_q, bad_j])
+        tie = (s_ours - s_ref).abs() <= 2e-6
+        ok_pos = ok_pos.clone()
+        ok_pos[bad_q[tie], bad_j[tie]] = True
+        settled = int(tie.sum())
+    ok_rows = ok_pos.all(dim=1) & ~value_bad.any(dim=1)
+    up_to_ties = int(ok_rows.sum())
     return {"queries": n, "identical": identical, "ties_within_1e-6": up_to_ties - identical,
             "mismatch": n - up_to_ties, "max_abs_score_diff": float((ours_v - bv).abs().max()),
-            "tie_tolerance": 2e-6, "reference": "torch fp32 F.normalize -> mm -> topk on the GPU, per shard, merged"}
+            "tie_tolerance": 2e-6, "value_tolerance": 5e-6, "swapped_positions_checked_in_float64": settled,
+            "reference": "torch fp32 F.normalize -> mm -> topk on the GPU, per shard, merged"}
 
 
 def run_ours(args):

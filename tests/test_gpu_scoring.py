@@ -701,3 +701,34 @@ def test_score_functions_called_directly_return_the_dense_matrix(score):
     if score == "cos_sim":
         mask, scores = qst_b200.dissimilar_mask(q[0].to(_dev()), c.to(_dev()), 0.2)
         assert mask.shape == (3001,) and torch.equal(mask, scores <= 0.2)
+
+
+def test_bench_parity_sample_counts_ties_and_mismatches():
+    """bench.py's in-run check: identical rankings pass, a swap inside a true tie is a tie (settled in
+    float64 when the two fp32 summation orders disagree by more than the tolerance), a wrong document is
+    a mismatch (the bench then exits non-zero)."""
+    import importlib.util, os
+    import qst_b200
+    from qst_b200 import comm
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(2)
+    q = torch.randn(64, 96, generator=g, device=dev)
+    c = torch.randn(5000, 96, generator=g, device=dev)
+    c[4001] = c[17] * 3.0                    # same direction, different norm: an exact cos_sim tie with row 17
+    res = qst_b200.topk(q, qst_b200.CorpusIndex(c, "cos_sim"), 20)
+    cm = comm.SingleComm()
+    ok = bench.parity_sample(cm, q, res.values, res.indices, c, 0, 20, n_sample=64)
+    assert ok["queries"] == 64 and ok["mismatch"] == 0 and ok["identical"] + ok["ties_within_1e-6"] == 64
+    wrong = res.indices.clone()
+    other = int(res.indices[5, -1]) + 1 if int(res.indices[5, -1]) + 1 < 5000 else 0
+    if other not in res.indices[5].tolist():
+        wrong[5, 3] = other                  # a document that is not in the top 20, reported with a top-20 score
+        bad = bench.parity_sample(cm, q, res.values, wrong, c, 0, 20, n_sample=64)
+        assert bad["mismatch"] == 1
+    vals_off = res.values.clone()
+    vals_off[7, 0] += 1e-3                   # a wrong VALUE with the right document is a mismatch too
+    off = bench.parity_sample(cm, q, vals_off, res.indices, c, 0, 20, n_sample=64)
+    assert off["mismatch"] == 1 and off["max_abs_score_diff"] > 5e-4

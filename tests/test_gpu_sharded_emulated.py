@@ -42,7 +42,7 @@ def _run(G, q, c, k, score, master, strategy="owners", owned=False, query_tile=1
 
 
 @pytest.mark.parametrize("score", ["cos_sim", "dot_score", "euclid_score"])
-@pytest.mark.parametrize("G,master", [(2, "sharded"), (4, "sharded"), (3, "sharded"), (4, "replicated")])
+@pytest.mark.parametrize("G,master", [(1, "sharded"), (2, "sharded"), (4, "sharded"), (3, "sharded"), (4, "replicated")])
 def test_sharded_topk_matches_unsharded_oracle(G, master, score):
     g = torch.Generator().manual_seed(100 + G)
     Q, N, D, k = 150, 30011, 96, 50
