@@ -1246,6 +1246,12 @@ extern "C" int qst_topk_plan_make(int64_t Q, int64_t N, int64_t D, int k, int kp
     if (ku <= 64 && plan->cap < 256) plan->cap = 256;
   }
   plan->grid = plan->units < groups_max ? plan->units : groups_max;  // CTA groups (x ctas CTAs)
+  {
+    // QST_K2_GROUPS: leave SMs free for kernels of a neighbouring batch running on another stream
+    // (spatial overlap experiments: K2 is persistent, nothing else becomes resident on an SM it holds)
+    const char* e = getenv("QST_K2_GROUPS");
+    if (e && atoi(e) >= 1 && atoi(e) < plan->grid) plan->grid = atoi(e);
+  }
   plan_layout(plan);
   return QST_OK;
 }
