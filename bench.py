@@ -660,6 +660,7 @@ def replicated_master_block(cm, dev, queries, n0, n1, rank, timed):
     ms, out, _ = timed(lambda: corp.topk_owned(queries, TOPK), 5)
     par = parity_sample(cm, queries, out[0], out[1], full[n0:n1], n0, TOPK)
     Q = Q_PER_GPU * cm.world
+    corp.close()
     return {"value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": 5,
             "per_gpu_fp32_master_gb": N_CORPUS * DIM * 4 / 1e9, "parity_sample": par}
 
@@ -696,6 +697,7 @@ def config4_block(cm, dev, rank, world, barrier, max_over_ranks):
     par = parity_sample(cm, own_q, vals, idx, rows_f32, n0, TOPK)
     stage = corp.stage_ms()
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    corp.close()           # the peer-mapped buffers (hints, query gather) are cudaMalloc'ed outside torch's pool
     return {"workload": f"{q_own * world} queries x {n_total} corpus x {DIM}, top-{TOPK}, {world} GPUs, fp32 master sharded",
             "value": q_own * world / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
             "k2_tflops_per_gpu": 2.0 * q_own * world * (n1 - n0) * DIM / (stage["K2"] * 1e-3) / 1e12,

@@ -279,6 +279,11 @@ def run_local_world(world: int, fn, *args):
         except BaseException as e:   # noqa: BLE001 -- re-raised below
             err.append(e)
             comms[r]._w.barrier.abort()
+        finally:
+            from . import scoring
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            scoring.release_workspaces()     # this thread's scratch buffers die with the thread
 
     threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
     for t in threads:

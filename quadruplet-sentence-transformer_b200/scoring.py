@@ -152,6 +152,17 @@ def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
     return ws
 
 
+def release_workspaces(thread_ident: Optional[int] = None) -> int:
+    """Drops the cached scratch buffers of one host thread (default: the calling one) -- or of every
+    thread with ``thread_ident=-1``.  The cache only ever grows otherwise (one buffer per purpose, device,
+    stream and thread, sized for the largest call seen).  Returns the number of buffers released."""
+    me = threading.get_ident() if thread_ident is None else thread_ident
+    keys = [k for k in _ws_cache if thread_ident == -1 or k[3] == me]
+    for k in keys:
+        del _ws_cache[k]
+    return len(keys)
+
+
 def make_plan(Q: int, N: int, D: int, k: int, kprime: int = 0, score: str = "cos_sim",
               sm_count: int = 0) -> _lib.TopkPlan:
     plan = _lib.TopkPlan()

@@ -223,6 +223,21 @@ class ShardedCorpus:
             self.global_stats = self.comm.all_reduce_max(self.index.rows.stats) if self.world > 1 \
                 else self.index.rows.stats
 
+    def close(self):
+        """Releases the peer-mapped buffers (threshold hints, query gather).  Collective in effect: call it
+        on every rank, after the last ``topk`` / ``topk_owned`` / ``finish_exact``."""
+        self.finish_exact()
+        dev = self.index.device
+        if self._peer_hints is not None or self._peer_gather is not None:
+            torch.cuda.synchronize(dev)
+            if self.world > 1:
+                self.comm.barrier()          # nobody may still be writing into a buffer that goes away
+        for holder in ("_peer_hints", "_peer_gather"):
+            obj = getattr(self, holder)
+            if obj is not None:
+                obj.close()
+                setattr(self, holder, None)
+
     @property
     def master_mode(self) -> str:
         return "replicated" if self.master is not None else "sharded"
