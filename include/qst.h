@@ -248,6 +248,16 @@ int qst_finalize_topk(const qst_topk_plan* plan, const void* workspace,
                       int64_t idx_offset, float* out_val, int64_t* out_idx, float* out_margin,
                       qst_stream_t stream);
 
+/* K3 in two passes: kprime_first (< plan->kprime) candidates are rescored for every query; the queries whose
+ * certificate then fails are finalised again with the plan's full k' (the others are left alone).  Same
+ * output as qst_finalize_topk, less data gathered (config 3: k' 176 then 224, 0.3 % of the queries take
+ * the second pass).  Needs q_err / c_stats / out_margin (the certificate decides who takes the second pass). */
+int qst_finalize_topk_adaptive(const qst_topk_plan* plan, int kprime_first, const void* workspace,
+                               const float* q_f32, const float* q_inv, const float* q_err,
+                               const float* c_f32, const float* c_inv, const float* c_stats,
+                               int64_t idx_offset, float* out_val, int64_t* out_idx, float* out_margin,
+                               qst_stream_t stream);
+
 /* ---- corpus-sharded retrieval, candidate exchange ----------------------
  * Step 1 on every shard, after qst_score_select: the m best candidates per query BY bf16 KEY, no
  * rescoring.  out_lists [Q, m+1] of 8-byte entries (ordered-uint key, uint32 global row id =

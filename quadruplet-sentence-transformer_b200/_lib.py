@@ -80,6 +80,7 @@ SIGNATURES = {
     "qst_peer_buffer_close": (_INT, [_P]),
     "qst_peer_buffer_destroy": (_INT, [_P]),
     "qst_finalize_topk": (_INT, [C.POINTER(TopkPlan), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "qst_finalize_topk_adaptive": (_INT, [C.POINTER(TopkPlan), _INT, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "qst_select_candidates": (_INT, [C.POINTER(TopkPlan), _P, _INT, _I64, _P, _P]),
     "qst_finalize_lists_scratch_bytes": (C.c_size_t, [_I64, _INT]),
     "qst_finalize_lists": (_INT, [_I64, _INT, _INT, _INT, _INT, _INT, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

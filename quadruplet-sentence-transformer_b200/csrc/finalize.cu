@@ -190,6 +190,8 @@ struct FinParams {
   uint32_t* bound_out;
   int req_G, req_m;
   int64_t n_total;
+  // refine mode: queries whose certificate already holds (out_margin[q] > 0 on entry) are left alone
+  int refine;
 };
 
 // balanced contiguous shards (sharded.shard_bounds): first n % G shards hold one row more
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = q / P.rows_per_unit, r = q % P.rows_per_unit;
+  if (P.refine && P.out_margin[q] > 0.f) return;   // certified by the first, narrower pass
 
   // stage the fp32 query row and its squared norm
   float qq = 0.f;
@@ -893,20 +896,57 @@ __global__ void unpack_list_trailers_kernel(const uint2* __restrict__ lists, int
 
 using namespace qst;
 
+static int finalize_topk_impl(const qst_topk_plan* plan, int kprime, int refine, const void* workspace, const float* q_f32,
+                              const float* q_inv, const float* q_err, const float* c_f32, const float* c_inv,
+                              const float* c_stats, int64_t idx_offset, float* out_val, int64_t* out_idx,
+                              float* out_margin, qst_stream_t stream);
+
 extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspace, const float* q_f32,
                                  const float* q_inv, const float* q_err, const float* c_f32, const float* c_inv,
                                  const float* c_stats, int64_t idx_offset, float* out_val, int64_t* out_idx,
                                  float* out_margin, qst_stream_t stream) {
+  QST_CHECK_ARG(plan != nullptr, "finalize_topk: null plan");
+  return finalize_topk_impl(plan, plan->kprime, 0, workspace, q_f32, q_inv, q_err, c_f32, c_inv, c_stats, idx_offset,
+                            out_val, out_idx, out_margin, stream);
+}
+
+// Two-pass K3: the first pass rescoring only `kprime_first` (< plan->kprime) candidates per query certifies
+// all but a fraction of a percent of the queries at config 3 (k' = 176: 33 of 10 000 left, against 14 % less
+// gathered data than k' = 224); the second pass repeats the work with the plan's full k' for the queries
+// whose margin is still <= 0 and leaves the others alone.  Same result as one pass with the full k':
+// a certified ranking is THE exact ranking whatever k' produced it.
+extern "C" int qst_finalize_topk_adaptive(const qst_topk_plan* plan, int kprime_first, const void* workspace,
+                                          const float* q_f32, const float* q_inv, const float* q_err,
+                                          const float* c_f32, const float* c_inv, const float* c_stats,
+                                          int64_t idx_offset, float* out_val, int64_t* out_idx, float* out_margin,
+                                          qst_stream_t stream) {
+  QST_CHECK_ARG(plan != nullptr && out_margin != nullptr, "finalize_topk_adaptive: null plan / margin");
+  QST_CHECK_ARG(q_err != nullptr && c_stats != nullptr, "finalize_topk_adaptive: needs the certificate inputs");
+  if (kprime_first < plan->k || kprime_first >= plan->kprime)
+    return finalize_topk_impl(plan, plan->kprime, 0, workspace, q_f32, q_inv, q_err, c_f32, c_inv, c_stats, idx_offset,
+                              out_val, out_idx, out_margin, stream);
+  int rc = finalize_topk_impl(plan, kprime_first, 0, workspace, q_f32, q_inv, q_err, c_f32, c_inv, c_stats, idx_offset,
+                              out_val, out_idx, out_margin, stream);
+  if (rc) return rc;
+  return finalize_topk_impl(plan, plan->kprime, 1, workspace, q_f32, q_inv, q_err, c_f32, c_inv, c_stats, idx_offset,
+                            out_val, out_idx, out_margin, stream);
+}
+
+static int finalize_topk_impl(const qst_topk_plan* plan, int kprime, int refine, const void* workspace, const float* q_f32,
+                              const float* q_inv, const float* q_err, const float* c_f32, const float* c_inv,
+                              const float* c_stats, int64_t idx_offset, float* out_val, int64_t* out_idx,
+                              float* out_margin, qst_stream_t stream) {
   QST_CHECK_ARG(plan && workspace && q_f32 && c_f32 && out_val && out_idx, "finalize_topk: null argument");
   QST_CHECK_ARG(plan->score != QST_SCORE_COS || (q_inv && c_inv), "finalize_topk: cos score needs inverse norms");
   QST_CHECK_ARG(plan->stripes <= kMaxStripes, "finalize_topk: too many stripes (%d)", plan->stripes);
   const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
   FinParams P{};
   P.Q = (int)plan->Q; P.N = (int)plan->N; P.D = (int)plan->D;
-  P.k = plan->k; P.kprime = plan->kprime; P.cap = plan->cap;
+  P.k = plan->k; P.kprime = kprime; P.cap = plan->cap;
+  P.refine = refine;
   P.m_tiles = plan->m_tiles; P.stripes = plan->stripes; P.score = plan->score;
   P.rows_per_unit = plan->rows_per_unit;
-  int sm_cap = plan->kprime + plan->cap;
+  int sm_cap = kprime + plan->cap;
   if (sm_cap < 4096) sm_cap = 4096;
   // many short stripes (small query batches): room for what every unit may leave per row, so the
   // gather stays a single parallel pass
@@ -919,7 +959,7 @@ extern "C" int qst_finalize_topk(const qst_topk_plan* plan, const void* workspac
   P.unit_cand = reinterpret_cast<const uint2*>(ws + plan->off_cand);
   P.q_f32 = q_f32; P.q_inv = q_inv; P.q_err = q_err; P.c_f32 = c_f32; P.c_inv = c_inv; P.c_stats = c_stats;
   P.idx_offset = idx_offset; P.out_val = out_val; P.out_idx = out_idx; P.out_margin = out_margin;
-  const size_t smem = (size_t)sm_cap * 8 + (size_t)plan->kprime * 8 + round_up((size_t)plan->D * 4, 16);
+  const size_t smem = (size_t)sm_cap * 8 + (size_t)kprime * 8 + round_up((size_t)plan->D * 4, 16);
   QST_CHECK_ARG(smem <= 200 * 1024, "finalize_topk: D=%lld too large for the rescoring stage", (long long)plan->D);
   QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   finalize_kernel<<<(unsigned)plan->Q, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
