@@ -17,9 +17,9 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libqst.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["common.cu", "quad_loss.cu", "quad_eval.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu",
+SOURCES = ["common.cu", "quad_loss.cu", "quad_loss_f32.cu", "quad_loss_f16.cu", "quad_loss_bf16.cu", "quad_eval.cu", "prep.cu", "score_select.cu", "finalize.cu", "metrics.cu",
            "comm.cu"]
-HEADERS = ["qst_common.cuh", "sm100_ptx.cuh", "select_common.cuh"]
+HEADERS = ["qst_common.cuh", "sm100_ptx.cuh", "select_common.cuh", "quad_loss_kernels.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB_PATH + ".tmp"
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"]
