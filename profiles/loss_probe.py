@@ -18,7 +18,7 @@ data = [[torch.randn(B, D, generator=g, device=dev) for _ in range(4)] for _ in 
 grads = [[torch.empty(B, D, device=dev) for _ in range(4)] for _ in range(sets)]
 src = [torch.randn(4 * B * D, generator=g, device=dev) for _ in range(sets)]
 dst = [torch.empty(4 * B * D, device=dev) for _ in range(sets)]
-loss = torch.empty(sets, device=dev)
+loss = torch.empty(sets * B, device=dev)
 ws = torch.zeros(lib.qst_quadruplet_workspace_bytes(), dtype=torch.uint8, device=dev)
 prm = quad_loss._params(0.6, 1.0, 0.5, 0.5, 2.0, False)
 
@@ -27,7 +27,7 @@ def fused(st, red):
     for i in range(sets):
         x, gr = data[i], grads[i]
         _lib.check(lib.qst_quadruplet_fwd_bwd(x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), x[3].data_ptr(),
-                                              _lib.QST_F32, B, D, C.byref(prm), red, 1.0, loss[i:].data_ptr(),
+                                              _lib.QST_F32, B, D, C.byref(prm), red, 1.0, loss[i * B:].data_ptr(),
                                               gr[0].data_ptr(), gr[1].data_ptr(), gr[2].data_ptr(),
                                               gr[3].data_ptr(), ws.data_ptr(), st))
 
@@ -46,19 +46,26 @@ def timeit(name, fn):
         with torch.cuda.graph(graph, stream=side):
             fn(torch.cuda.current_stream(dev).cuda_stream)
     torch.cuda.current_stream(dev).wait_stream(side)
-    for _ in range(3):
-        graph.replay()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(20):
-        graph.replay()
-    b.record()
-    torch.cuda.synchronize()
-    us = a.elapsed_time(b) * 1e3 / (20 * sets)
-    print(f"{name:34s} {us:7.2f} us/launch  {8 * B * D * 4 / us / 1e3:7.0f} GB/s")
+    import pynvml
+    blocks = []
+    for blk in range(8):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        mhz = pynvml.nvmlDeviceGetClockInfo(NV, pynvml.NVML_CLOCK_SM)
+        blocks.append((a.elapsed_time(b) * 1e3 / (20 * sets), mhz))
+    us = sorted(x for x, _ in blocks)[len(blocks) // 2]
+    print(f"{name:34s} median {us:7.2f} us/launch  {8 * B * D * 4 / us / 1e3:7.0f} GB/s   blocks: "
+          + " ".join(f"{x:.2f}@{m}" for x, m in blocks))
 
 
+import pynvml
+pynvml.nvmlInit()
+NV = pynvml.nvmlDeviceGetHandleByIndex(0)
 timeit("torch copy 50MB->50MB", copies)
-timeit("fused loss mean (reg path)", lambda st: fused(st, _lib.QST_RED_MEAN))
-timeit("fused loss none (no reduction)", lambda st: fused(st, _lib.QST_RED_NONE))
+for rep in range(2):
+    timeit("fused loss mean (reg path)", lambda st: fused(st, _lib.QST_RED_MEAN))
+    timeit("fused loss none (no reduction)", lambda st: fused(st, _lib.QST_RED_NONE))
