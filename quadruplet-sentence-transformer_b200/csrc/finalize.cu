@@ -396,6 +396,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
           if (sq) eps += 1e-5f * cn * cn;   // fp32 evaluation of ||c||^2 and of the exact distance
         }
         margin = kth - (t_bf + eps);
+        // exactly 0 (e.g. an all-zero query: every score is 0) is "not certified" like any other
+        // non-positive margin; the value 0 itself is reserved for rescan_emit_kernel's mark
+        if (margin == 0.f) margin = -1e-30f;
       }
       P.out_margin[q] = margin;
     }
@@ -819,6 +822,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_exact_kernel(int Q, int 
           if (sq) eps += 1e-5f * cn * cn;
         }
         margin = kth - (t_bf + eps);
+        if (margin == 0.f) margin = -1e-30f;   // 0 is the re-scan's "cannot be repaired" mark
       }
       out_margin[q] = margin;
     }

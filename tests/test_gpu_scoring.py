@@ -732,3 +732,66 @@ def test_bench_parity_sample_counts_ties_and_mismatches():
     vals_off[7, 0] += 1e-3                   # a wrong VALUE with the right document is a mismatch too
     off = bench.parity_sample(cm, q, vals_off, res.indices, c, 0, 20, n_sample=64)
     assert off["mismatch"] == 1 and off["max_abs_score_diff"] > 5e-4
+
+
+@pytest.mark.parametrize("score", ["cos_sim", "dot_score", "euclid_score"])
+@pytest.mark.parametrize("D", [1, 3, 100])
+def test_degenerate_rows_zero_vectors_collisions_odd_widths(score, D):
+    """What the reference's arithmetic does with rows it was not written for: all-zero query and document
+    rows (``F.normalize`` divides by max(norm, 1e-12) -> a zero row scores 0 against everything),
+    duplicated documents (exact score collisions: the lower corpus position ranks first), rows of 1, 3
+    and 100 elements (padding of the bf16 operands), a single query, a single document."""
+    import qst_b200
+    g = torch.Generator().manual_seed(1000 + D)
+    q = torch.randn(19, D, generator=g)
+    c = torch.randn(301, D, generator=g)
+    q[3] = 0
+    c[5] = 0
+    c[7] = c[9] = c[200]
+    k = 10
+    for qq, cc in ((q, c), (q[:1], c), (q, c[:1]), (q[3:4], c[5:6])):
+        n = min(k, cc.shape[0])
+        want_val, want_idx = _oracle_topk(qq, cc, n, score)
+        if score == "euclid_score":
+            # distances near 0 (a query next to a document in 1-3 dimensions): torch.cdist's matmul
+            # formulation cancels catastrophically on the host, so the yardstick is the definition in
+            # float64 (the same arbitration assert_same_ranking applies to euclid_score)
+            want_val = (1 / (1 + torch.cdist(qq.double(), cc.double(), compute_mode="donot_use_mm_for_euclid_dist")
+                             )).topk(n, dim=1).values.float()
+        res = qst_b200.topk(qq.to(_dev()), qst_b200.CorpusIndex(cc.to(_dev()), score), k)
+        got_val, got_idx = res.values.cpu(), res.indices.cpu()
+        assert torch.isfinite(got_val[:, :n]).all()
+        scale = max(float(want_val.abs().max()), 1.0) if score == "dot_score" else 1.0
+        torch.testing.assert_close(got_val[:, :n] / scale, want_val / scale, rtol=0, atol=2e-6)
+        # ids: the documents returned must carry the returned scores (ties make the id set ambiguous)
+        dense = {"cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score,
+                 "euclid_score": qst_b200.euclidean_score}[score](qq.to(_dev()), cc.to(_dev())).cpu()
+        assert torch.equal(torch.gather(dense, 1, got_idx[:, :n]), got_val[:, :n])
+        assert bool((got_idx[:, n:] == -1).all())
+        # collisions and all-equal rows: among equal scores the lower position comes first
+        same = got_val[:, 1:n] == got_val[:, :n - 1]
+        assert bool((got_idx[:, 1:n][same] > got_idx[:, :n - 1][same]).all())
+        assert bool((res.margin > 0).all())
+
+
+def test_no_queries_and_non_contiguous_inputs():
+    """Zero queries give empty results (the reference's loops simply do not run); strided views and
+    half-precision embeddings are accepted like torch accepts them."""
+    import qst_b200
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(500, 64, generator=g)
+    index = qst_b200.CorpusIndex(c.to(_dev()))
+    res = qst_b200.topk(torch.empty(0, 64, device=_dev()), index, 10)
+    assert res.values.shape == (0, 10) and res.indices.shape == (0, 10)
+    wide = torch.randn(40, 128, generator=g)
+    q = wide[:, ::2]                                  # stride 2
+    want_val, want_idx = _oracle_topk(q.contiguous(), c, 10)
+    res = qst_b200.topk(q.to(_dev()), index, 10)
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, "strided queries")
+    res = qst_b200.topk(wide.to(_dev())[:, ::2], index, 10)
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, "strided device view")
+    # fp16 embeddings (model.half()): scored from their fp32 up-cast, like torch.mm on .float()
+    qh = q.half()
+    want_val, want_idx = _oracle_topk(qh.float(), c, 10)
+    res = qst_b200.topk(qh.to(_dev()), index, 10)
+    assert_same_ranking(res.indices, res.values, want_idx, want_val, "fp16 queries")

@@ -142,3 +142,24 @@ def test_deferred_certificate_check_patches_results_in_place():
         for v, i, m in ((v1, i1, m1), (v2, i2, m2)):
             assert_same_ranking(i, v, want_idx[lo:hi], want_val[lo:hi], f"deferred rank {rank}")
             assert bool((m > 0).all())
+
+
+@pytest.mark.parametrize("master", ["sharded", "replicated"])
+def test_sharded_all_zero_query_and_duplicated_documents(master):
+    """An all-zero query scores 0 against every document of every shard (a corpus-wide exact tie, margin
+    exactly 0 in the first pass) and duplicated documents straddle the shard boundary: the distributed
+    re-scan must settle both towards the lower global position."""
+    g = torch.Generator().manual_seed(11)
+    Q, N, D, k, G = 12, 900, 48, 10, 3
+    q = torch.randn(Q, D, generator=g)
+    c = torch.randn(N, D, generator=g)
+    q[4] = 0
+    c[299] = c[300] = c[650]            # shard boundaries at 300 and 600
+    q[5] = c[300] + 0.01 * torch.randn(D, generator=g)
+    want_val, _ = _oracle_topk(q, c, k, "cos_sim")
+    out = _run(G, q, c, k, "cos_sim", master)
+    for rank, (v, i, m, _) in enumerate(out):
+        torch.testing.assert_close(v, want_val, rtol=0, atol=2e-6)
+        assert bool((m > 0).all()), f"{master} rank {rank}: {m}"
+        assert i[4].tolist() == list(range(k)), "all scores tie at 0: the k lowest positions, in order"
+        assert i[5, :3].tolist() == [299, 300, 650]
