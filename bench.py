@@ -55,6 +55,7 @@ Q_PER_GPU = 10_000
 N_CORPUS = 1_000_000
 DIM = 768
 TOPK = 100
+NO_PREFETCH = bool(os.environ.get("QST_BENCH_NO_PREFETCH"))   # A/B switch: sharded steps without topk_owned(prefetch=)
 CPU_SAMPLE_Q = 1000
 SLAB = 125_000            # the synthetic corpus is generated slab by slab, slab i from seed CORPUS_SEED + i
 CORPUS_SEED = 14 + 1000
@@ -474,7 +475,9 @@ def run_ours(args):
         if corp is not None:
             # exact="deferred": the certificate check of a step (one host read) is made when the NEXT step
             # is submitted, the last one inside timed() -- every step is checked within the timed region
-            return corp.topk_owned(queries, TOPK, exact="deferred")
+            # prefetch=: the NEXT batch (here the same 10 000 rows again) is prepared and distributed
+            # underneath this step's exchanges, every step, so no step waits for an all-gather before K2
+            return corp.topk_owned(queries, TOPK, exact="deferred", prefetch=None if NO_PREFETCH else queries)
         r = scoring.topk(queries, index, TOPK)
         return r.values, r.indices, r.margin
 
@@ -553,7 +556,8 @@ def run_ours(args):
     for st_ in pipe.streams:
         st_.wait_event(e0)
     for _ in range(steps):
-        ticket = pipe.submit(queries_host)
+        # sharded: the next batch (the same pinned rows again) is copied in and announced one step ahead
+        ticket = pipe.submit(queries_host, queries_host) if (corp is not None and not NO_PREFETCH) else pipe.submit(queries_host)
     for st_ in pipe.streams:
         cur.wait_stream(st_)
     e1.record(cur)
@@ -566,7 +570,7 @@ def run_ours(args):
 
     # ---- secondary measurements (never allowed to break the headline line) -----------------------
     secondary = {}
-    if world > 1:
+    if world > 1 and not os.environ.get("QST_BENCH_SKIP_SECONDARY"):
         for name, fn in (("replicated_master", lambda: replicated_master_block(cm, dev, queries, n0, n1, rank, timed)),
                          ("config4", lambda: config4_block(cm, dev, rank, world, barrier, max_over_ranks))):
             try:
@@ -680,15 +684,16 @@ def config4_block(cm, dev, rank, world, barrier, max_over_ranks):
     qgen = torch.Generator(device=dev).manual_seed(14 + 500 + rank)
     own_q = torch.randn(q_own, DIM, generator=qgen, device=dev)
     corp.enable_stage_timing()
+    nxt = None if NO_PREFETCH else own_q
     for _ in range(2):
-        out = corp.topk_owned(own_q, TOPK, exact="deferred")
+        out = corp.topk_owned(own_q, TOPK, exact="deferred", prefetch=nxt)
     corp.finish_exact()
     barrier()
     steps = 2
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        out = corp.topk_owned(own_q, TOPK, exact="deferred")
+        out = corp.topk_owned(own_q, TOPK, exact="deferred", prefetch=nxt)
     corp.finish_exact()            # certificate check of the last step, inside the timed region
     e1.record()
     barrier()
@@ -735,7 +740,8 @@ def config5_block(cm, corp, dev, rank, world, barrier, max_over_ranks):
         ranked = torch.empty((q_own, TOPK), dtype=torch.long, device=dev)
         bad = 0
         for s0 in range(0, q_own, batch):
-            v, i, m = corp.topk_owned(own_q[s0:s0 + batch], TOPK)
+            nxt = own_q[s0 + batch:s0 + 2 * batch] if (s0 + batch < q_own and not NO_PREFETCH) else None
+            v, i, m = corp.topk_owned(own_q[s0:s0 + batch], TOPK, prefetch=nxt)
             ranked[s0:s0 + batch] = i
             bad = bad + (~(m > 0)).sum()
         return ranked, metrics.per_query_metrics(ranked, rowptr, cols, ks), bad

@@ -149,8 +149,10 @@ def check(rc: int) -> None:
 
 
 def ptr(t) -> int:
-    """Device pointer of a torch tensor (or None -> NULL)."""
-    return None if t is None else t.data_ptr()
+    """Device pointer of a torch tensor (None -> NULL; an int is taken as a raw device pointer)."""
+    if t is None or isinstance(t, int):
+        return t
+    return t.data_ptr()
 
 
 def stream_ptr(device=None) -> int:

@@ -225,9 +225,10 @@ class _LocalWorld:
 
 
 class LocalComm(Comm):
-    """Rank of a node emulated by threads of ONE process on ONE device.  Every thread must issue its
-    CUDA work on the same stream (the default stream of the device: work is then totally ordered in
-    submission order, and a host-side barrier between "deposit" and "read" is all a collective needs)."""
+    """Rank of a node emulated by threads of ONE process on ONE device.  A collective is "deposit,
+    host barrier, read, host barrier"; the depositor's stream is drained before the deposit and the
+    reader's stream after the read, so the threads may work on any streams (the double-buffered host
+    pipeline uses one per slot).  A test shim: correctness of the sharded protocol, not speed."""
 
     def __init__(self, shared: _LocalWorld, rank: int):
         self._w, self.world, self.rank = shared, shared.world, rank
@@ -237,25 +238,31 @@ class LocalComm(Comm):
         shared = _LocalWorld(world)
         return [LocalComm(shared, r) for r in range(world)]
 
-    def _exchange(self, obj):
+    @staticmethod
+    def _drain(obj):
+        if isinstance(obj, torch.Tensor) and obj.is_cuda:
+            torch.cuda.current_stream(obj.device).synchronize()
+
+    def _exchange(self, obj, read=list):
         w = self._w
+        self._drain(obj)          # what is deposited (and every peer write queued before it) is complete
         w.slots[self.rank] = obj
         w.barrier.wait()
-        got = list(w.slots)
+        out = read(list(w.slots))
+        self._drain(obj)          # the reads have happened before a depositor may reuse its memory
         w.barrier.wait()          # nobody overwrites a slot before everybody has read it
-        return got
+        return out
 
     def all_gather(self, t):
-        return torch.cat([x for x in self._exchange(t.contiguous())])
+        return self._exchange(t.contiguous(), lambda got: torch.cat(got))
 
     def all_to_all(self, t):
         t = t.contiguous()
         n = t.shape[0] // self.world
-        got = self._exchange(t)
-        return torch.cat([x[self.rank * n:(self.rank + 1) * n] for x in got])
+        return self._exchange(t, lambda got: torch.cat([x[self.rank * n:(self.rank + 1) * n] for x in got]))
 
     def all_reduce_max(self, t):
-        return torch.stack(self._exchange(t)).amax(dim=0)
+        return self._exchange(t, lambda got: torch.stack(got).amax(dim=0))
 
     def barrier(self):
         self._w.barrier.wait()

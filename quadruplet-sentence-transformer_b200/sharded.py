@@ -34,7 +34,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -133,46 +133,61 @@ class PeerHints:
 
 
 class PeerGather:
-    """All-gather of one fp32 block per rank through the COPY ENGINES into peer-mapped buffers.
+    """All-gather of one block per rank and REGION through the COPY ENGINES into peer-mapped buffers
+    (regions: the fp32 queries, their bf16 tensor-core operand, their inverse norms).
 
     The sharded-master path needs the fp32 queries of every rank on every rank -- but only after K2, for
     the exact rescoring.  An NCCL all-gather would sit on the critical path in front of K2 (its kernel
     cannot become resident beside the persistent K2); copy-engine transfers use no SM and run underneath
     K2.  Every rank pushes its block into the gather buffer of every rank on a side stream; the consumer
-    kernel is ordered after (a) this rank's own pushes (event) and (b) a later collective of the same
-    step in which every rank takes part only after ITS pushes have completed (the all-to-all of the
-    candidate lists) -- so every block has landed.  Two generations alternate between steps: a rank can
-    be at most one step ahead of another (there are collectives in every step), so a fast rank never
-    writes into a buffer a slow rank is still reading."""
+    kernel is ordered after (a) this rank's own pushes (event) and (b) a later collective in which every
+    rank takes part only after ITS pushes have completed -- so every block has landed.  A step that knows
+    the NEXT batch (``topk_owned(..., prefetch=)``) pushes all three regions of that batch while its own
+    exchanges run, and the next step starts K2 straight from the gathered buffers: no collective in front
+    of K2 at all.  Two generations alternate between pushes: a rank can be at most one step ahead of
+    another (there are collectives in every step), so a fast rank never writes into a buffer a slow rank
+    is still reading."""
 
-    def __init__(self, block_bytes: int, comm: Comm, device: torch.device, own_stream: bool):
-        self.block_bytes, self.comm, self.device = block_bytes, comm, device
-        self.gen_bytes = ((block_bytes * comm.world + 255) // 256) * 256
+    def __init__(self, region_bytes: Sequence[int], comm: Comm, device: torch.device, own_stream: bool):
+        self.region_bytes, self.comm, self.device = tuple(int(b) for b in region_bytes), comm, device
+        self.region_off, off = [], 0
+        for b in self.region_bytes:
+            self.region_off.append(off)
+            off += ((b * comm.world + 255) // 256) * 256
+        self.gen_bytes = off
         self.buffers = comm.shared_buffers(2 * self.gen_bytes, device)
         self.ok = self.buffers is not None
         self.side = torch.cuda.Stream(device=device) if (self.ok and own_stream) else None
         self.step = 0
 
-    def push(self, block: torch.Tensor):
-        """Start pushing `block` (this rank's contiguous fp32 block) to every rank; returns
-        (pointer of this rank's gathered buffer for this step, event to wait for before the collective
-        that publishes the pushes)."""
+    def push(self, blocks: Sequence[Optional[torch.Tensor]], after: Optional[torch.cuda.Event] = None):
+        """Start pushing this rank's contiguous block of every region (``None``: that region is not used
+        in this generation) to every rank, after ``after`` (default: everything queued so far on the
+        current stream).  Returns (this rank's gathered-buffer pointer per region for this generation,
+        event to wait for before the collective that publishes the pushes)."""
         lib = _lib.load()
         off = (self.step % 2) * self.gen_bytes
         self.step += 1
         main = torch.cuda.current_stream(self.device)
         st = self.side if self.side is not None else main
         if st is not main:
-            st.wait_stream(main)                       # the block has been produced on the main stream
-        dst_off = off + self.comm.rank * self.block_bytes
+            if after is not None:
+                st.wait_event(after)
+            else:
+                st.wait_stream(main)                   # the blocks have been produced on the main stream
         with torch.cuda.stream(st):
-            for base in [self.buffers.local] + list(self.buffers.peers):
-                _lib.check(lib.qst_peer_copy(C.c_void_p(base + dst_off), block.data_ptr(), self.block_bytes,
-                                             st.cuda_stream))
+            for block, nbytes, roff in zip(blocks, self.region_bytes, self.region_off):
+                if block is None:
+                    continue
+                if block.numel() * block.element_size() != nbytes or not block.is_contiguous():
+                    raise ValueError("PeerGather.push: block does not match its region")
+                dst_off = off + roff + self.comm.rank * nbytes
+                for base in [self.buffers.local] + list(self.buffers.peers):
+                    _lib.check(lib.qst_peer_copy(C.c_void_p(base + dst_off), block.data_ptr(), nbytes, st.cuda_stream))
+                block.record_stream(st)
             ev = torch.cuda.Event()
             ev.record(st)
-        block.record_stream(st)
-        return self.buffers.local + off, ev
+        return [self.buffers.local + off + roff for roff in self.region_off], ev
 
     def close(self):
         if self.buffers is not None:
@@ -211,6 +226,7 @@ class ShardedCorpus:
         self.master = None
         self.last_rescanned = 0      # queries repaired by the distributed exact re-scan in the last call
         self._pending = None         # deferred certificate check of the last call (exact="deferred")
+        self._prefetched = None      # next batch, already prepared and distributed (topk_owned(prefetch=))
         if full_master is not None:
             if full_master.shape[0] != n_total:
                 raise ValueError(f"full_master must have {n_total} rows, got {full_master.shape[0]}")
@@ -227,6 +243,7 @@ class ShardedCorpus:
         """Releases the peer-mapped buffers (threshold hints, query gather).  Collective in effect: call it
         on every rank, after the last ``topk`` / ``topk_owned`` / ``finish_exact``."""
         self.finish_exact()
+        self._prefetched = None
         dev = self.index.device
         if self._peer_hints is not None or self._peer_gather is not None:
             torch.cuda.synchronize(dev)
@@ -290,17 +307,20 @@ class ShardedCorpus:
                 return None
         return self._peer_hints
 
-    def _gather_for(self, block_bytes: int, dev) -> Optional[PeerGather]:
-        """Copy-engine gather buffers for blocks of `block_bytes` (collective on first use / resize)."""
+    def _gather_for(self, q_own: int, dev) -> Optional[PeerGather]:
+        """Copy-engine gather buffers for `q_own` query rows per rank: regions fp32 rows / bf16 operand /
+        inverse norms (collective on first use / resize)."""
         if self._peer_gather_off or self.world == 1:
             return None
-        if self._peer_gather is None or self._peer_gather.block_bytes != block_bytes:
+        D, d_pad = self.index.d, self.index.rows.bf16.shape[1]
+        regions = (q_own * D * 4, q_own * d_pad * 2, q_own * 4)
+        if self._peer_gather is None or self._peer_gather.region_bytes != regions:
             if self._peer_gather is not None:
                 torch.cuda.synchronize(dev)
                 self.comm.barrier()
                 self._peer_gather.close()
             from .comm import LocalComm
-            self._peer_gather = PeerGather(block_bytes, self.comm, dev, own_stream=not isinstance(self.comm, LocalComm))
+            self._peer_gather = PeerGather(regions, self.comm, dev, own_stream=not isinstance(self.comm, LocalComm))
             if not self._peer_gather.ok:
                 self._peer_gather_off = True
                 return None
@@ -331,7 +351,8 @@ class ShardedCorpus:
         return "  ".join(f"{n} {v:.3f}" for n, v in self.stage_ms().items())
 
     # ---- the data-parallel entry: every rank brings the queries it owns ---------------------------
-    def topk_owned(self, own_queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True):
+    def topk_owned(self, own_queries: torch.Tensor, k: int, kprime: int = 0, exact: bool = True,
+                   prefetch: Optional[torch.Tensor] = None):
         """Collective: every rank passes ITS OWN slice of the query batch (same number of rows on
         every rank; global query id = rank * rows + i) and gets the exact global top-k of that slice
         back: (values [q_own, k], global ids [q_own, k], margins [q_own]).
@@ -354,12 +375,21 @@ class ShardedCorpus:
         ``finish_exact()``, whichever comes first -- by then the flag has long arrived, nothing stalls --
         and patches the returned tensors in place in the rare case a re-scan is needed.  A stream of
         batches should use it and call ``finish_exact()`` after the last one.
+
+        ``prefetch`` (sharded master, peer-mapped buffers available): this rank's slice of the NEXT batch
+        -- same shape on every rank, and every rank passes one or none.  Its K1 and the distribution of
+        its fp32 rows / bf16 operand / inverse norms to all ranks (copy engines, no SM) run on a side
+        stream while this call's exchanges and exact rescoring occupy the main stream, so the next call
+        -- when it is given that very tensor, unmodified -- starts K2 at once instead of after an
+        all-gather (any other tensor: the prefetched batch is discarded; like every collective, all
+        ranks must make the same sequence of calls).  A query set processed in tiles passes tile t+1
+        while asking for tile t.
         """
         if exact == "deferred" and (self.master is not None or self.world == 1):
             exact = True        # the replicated-master / single-GPU re-scans are device-driven: nothing to defer
         if self.master is not None:
             return self._topk_owned_replicated(own_queries, k, kprime, exact)
-        return self._topk_owned_sharded(own_queries, k, kprime, exact)
+        return self._topk_owned_sharded(own_queries, k, kprime, exact, prefetch)
 
     def _select_pass(self, q_bf16, q_pad, k, kprime, marks):
         """K2 on the local shard for all q_pad queries + the per-query candidate lists by bf16 key.
@@ -383,11 +413,11 @@ class ShardedCorpus:
         ws = self._ws(plan.ws_bytes, "select")
         if hints is not None:
             local, peers, n_peers = hints.launch_args()
-            _lib.check(lib.qst_score_select_peers(C.byref(plan), q_bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+            _lib.check(lib.qst_score_select_peers(C.byref(plan), _lib.ptr(q_bf16), self.index.rows.bf16.data_ptr(),
                                                   ws.data_ptr(), local, peers, n_peers, st))
             hints.advance(st)
         else:
-            _lib.check(lib.qst_score_select(C.byref(plan), q_bf16.data_ptr(), self.index.rows.bf16.data_ptr(),
+            _lib.check(lib.qst_score_select(C.byref(plan), _lib.ptr(q_bf16), self.index.rows.bf16.data_ptr(),
                                             ws.data_ptr(), st))
         self._mark(marks, "K2")
         lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
@@ -396,11 +426,37 @@ class ShardedCorpus:
         return lists, m, kprime_all
 
     # ---- fp32 master sharded: requests to the shards, exact scores back ----------------------------
-    def _topk_owned_sharded(self, own_queries, k, kprime, exact):
+    @staticmethod
+    def _tensor_key(t: torch.Tensor):
+        return (t.data_ptr(), tuple(t.shape), t.dtype, t._version)
+
+    def _start_prefetch(self, nxt: torch.Tensor, gather: PeerGather, after: torch.cuda.Event):
+        """K1 of the next batch's slice + copy-engine pushes of all three regions, on the gather's side
+        stream, ordered after `after` (this step's K2 + candidate selection)."""
+        dev = self.index.device
+        score = self.score
+        main = torch.cuda.current_stream(dev)
+        side = gather.side if gather.side is not None else main
+        if side is not main:
+            side.wait_event(after)
+        with torch.cuda.stream(side):
+            pq = scoring.prepare_rows(nxt.to(dev).float().contiguous(), scoring.QUERY_PREP[score])
+            k1_done = torch.cuda.Event()
+            k1_done.record(side)
+        for t in (pq.f32, pq.bf16, pq.inv_norm, pq.err):
+            if t is not None:
+                t.record_stream(main)
+        ptrs, pushed = gather.push([pq.f32, pq.bf16, pq.inv_norm if score == "cos_sim" else None], after=k1_done)
+        self._prefetched = (self._tensor_key(nxt), nxt.shape[0], pq, ptrs, pushed)
+
+    def _topk_owned_sharded(self, own_queries, k, kprime, exact, prefetch=None):
         lib = _lib.load()
         dev = self.index.device
         comm, G, r = self.comm, self.world, self.rank
         self.finish_exact()                 # the previous call's deferred certificate check, if any
+        pre, self._prefetched = getattr(self, "_prefetched", None), None
+        if pre is not None and pre[0] != self._tensor_key(own_queries):
+            pre = None      # not the batch that was announced (or modified since): discarded, plain path
         own_queries = own_queries.to(dev)
         q_own = own_queries.shape[0]
         q_pad = q_own * G
@@ -415,19 +471,30 @@ class ShardedCorpus:
             # Every rank rescoring rows of ITS shard needs the fp32 queries of all ranks -- but only
             # AFTER K2.  With peer-mapped buffers they are pushed by the copy engines underneath K2 and
             # only the bf16 operands (+ inverse norms) are all-gathered in front of it; without, the fp32
-            # queries are all-gathered and K1 runs on all of them locally.
-            own_f32 = own_queries.float().contiguous()
-            gather = self._gather_for(q_own * D * 4, dev) if G > 1 else None
-            if gather is not None:
+            # queries are all-gathered and K1 runs on all of them locally.  A batch the previous call
+            # prefetched is already here in full.
+            gather = self._gather_for(q_own, dev) if G > 1 else None
+            if prefetch is not None and (gather is None or prefetch.shape[0] != q_own):
+                prefetch = None             # no peer-mapped buffers (or a last, shorter tile): plain path next time
+            if pre is not None:
+                _, _, pq_own, (q_all_ptr, q_bf16, q_inv_all), _ = pre   # published by the previous call's last exchange
+                if not cos:
+                    q_inv_all = None
+                pushed = None
+                own_f32_ptr, own_err_ptr = pq_own.f32.data_ptr(), pq_own.err.data_ptr()
+                keep = (pq_own,)
+            elif gather is not None:
+                own_f32 = own_queries.float().contiguous()
                 pq_own = scoring.prepare_rows(own_f32, scoring.QUERY_PREP[score])
                 q_bf16 = comm.all_gather(pq_own.bf16)
                 q_inv_all = comm.all_gather(pq_own.inv_norm) if cos else None
                 # pushed AFTER the all-gathers are queued (the side stream waits for them): the pushes then
                 # share NVLink with nothing and run entirely underneath K2
-                q_all_ptr, pushed = gather.push(pq_own.f32)
+                (q_all_ptr, _, _), pushed = gather.push([pq_own.f32, None, None])
                 own_f32_ptr, own_err_ptr = pq_own.f32.data_ptr(), pq_own.err.data_ptr()
                 keep = (pq_own, q_bf16, q_inv_all)
             else:
+                own_f32 = own_queries.float().contiguous()
                 q_all = comm.all_gather(own_f32) if G > 1 else own_f32
                 pq = scoring.prepare_rows(q_all, scoring.QUERY_PREP[score])
                 own = slice(r * q_own, (r + 1) * q_own)
@@ -436,6 +503,10 @@ class ShardedCorpus:
                 keep = (pq,)
             self._mark(marks, "gather_q+prep")
             lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks)
+            if prefetch is not None:
+                sel_done = torch.cuda.Event()
+                sel_done.record()
+                self._start_prefetch(prefetch, gather, sel_done)
             if pushed is not None:
                 # this rank's pushes are done before it enters the exchange; the exchange completes only
                 # after every rank has entered it, i.e. after every rank's pushes are done
@@ -455,6 +526,9 @@ class ShardedCorpus:
                                                 _lib.ptr(q_inv_all), c.f32.data_ptr(),
                                                 c.inv_norm.data_ptr() if cos else None, exact_out.data_ptr(), st))
             self._mark(marks, "rescore")
+            if prefetch is not None:
+                # the next batch's pushes (started after K2, long done) are published by this exchange
+                torch.cuda.current_stream(dev).wait_event(self._prefetched[4])
             exact_in = comm.all_to_all(exact_out) if G > 1 else exact_out         # [G shards, q_own, m]
             vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
@@ -650,23 +724,37 @@ class ShardedHostPipeline:
         self._out = [None] * depth
         self._keep = [None] * depth
         self._kernels = None               # event: kernels of the most recent step have been queued and run
+        self._announced = None             # (host tensor, its version, device copy) of the batch announced last
         self._next = 0
 
-    def submit(self, own_queries_host: torch.Tensor) -> int:
+    def submit(self, own_queries_host: torch.Tensor, next_queries_host: Optional[torch.Tensor] = None) -> int:
+        """``next_queries_host``: the pinned slice the NEXT submit will bring (same rows on every rank, all
+        ranks or none).  It is copied in now and announced to ``topk_owned(prefetch=)``, so its K1 and
+        its distribution over the ranks run underneath this step's exchanges."""
         slot = self._next % len(self._streams)
         if self._done[slot] is not None:
             self._done[slot].synchronize()
         dev = self.corp.index.device
         st = self._streams[slot]
         with torch.cuda.stream(st):
-            q_dev = own_queries_host.to(dev, non_blocking=True)      # overlaps the previous step's kernels
+            ann, self._announced = self._announced, None
+            if ann is not None and ann[0] is own_queries_host and ann[1] == own_queries_host._version:
+                q_dev = ann[2]                                       # copied in by the previous submit
+                q_dev.record_stream(st)
+            else:
+                q_dev = own_queries_host.to(dev, non_blocking=True)  # overlaps the previous step's kernels
+            nxt_dev = None
+            if next_queries_host is not None and self.corp.master is None and self.corp.world > 1:
+                nxt_dev = next_queries_host.to(dev, non_blocking=True)
+                self._announced = (next_queries_host, next_queries_host._version, nxt_dev)
             if self._kernels is not None:
                 st.wait_event(self._kernels)
             # the distributed exact re-scan needs a host decision ("is anything flagged, anywhere?"),
             # which would stall the pipeline every step: run the first pass only, ship the global flag
             # to the host with the results, and repair in result() in the (rare) case it is set
             deferred = self.exact and self.corp.master is None and self.corp.world > 1
-            vals, idx, margin = self.corp.topk_owned(q_dev, self.k, self.kprime, self.exact and not deferred)
+            vals, idx, margin = self.corp.topk_owned(q_dev, self.k, self.kprime, self.exact and not deferred,
+                                                     **({"prefetch": nxt_dev} if nxt_dev is not None else {}))
             flag = None
             if deferred:
                 flag = self.corp.comm.all_reduce_max((~(margin > 0)).any().to(torch.float32).view(1))

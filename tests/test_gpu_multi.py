@@ -54,6 +54,15 @@ def _worker(rank, world, port, out_dir):
             torch.testing.assert_close(v2.cpu()[: hi_real - lo], want_val[lo:hi_real], rtol=0, atol=2e-6)
             assert (i2.cpu()[: hi_real - lo] != want_idx[lo:hi_real]).float().mean() < 1e-3
             assert bool((m2 > 0).all())
+            if full is None:
+                # a stream of batches, each announced one call ahead (K1 + copy-engine distribution of
+                # batch t+1 underneath the exchanges of batch t): same rankings, and the path was taken
+                own = qp[lo:hi].to(dev)
+                for t in range(3):
+                    v3, i3, m3 = corp.topk_owned(own, k, exact="deferred", prefetch=own if t < 2 else None)
+                    assert (corp._prefetched is not None) == (t < 2), "peer-mapped buffers must exist on one node"
+                    corp.finish_exact()
+                    assert torch.equal(v3, v2) and torch.equal(i3, i2) and bool((m3 > 0).all())
         # the same retrieval with NCCL called through the C ABI (qst_comm_*), no torch.distributed on the data path
         from qst_b200 import comm
         nc = comm.NcclComm.from_torch(dev)

@@ -34,6 +34,18 @@ def _fp64_scores(q, c, idx, score):
     return 1 / (1 + (qq[:, None, :] - cc).norm(dim=2))
 
 
+def assert_euclid_dense_close(got, q, c, oracle):
+    """Dense euclid_score matrix: within 2e-6 of the float64 definition, and as close to the CPU oracle
+    (torch.cdist's matmul formulation, whose accuracy depends on the host CPU's matmul path: a few GPU
+    boxes' hosts are off by up to 3e-5) as the oracle is to float64."""
+    truth = 1 / (1 + torch.cdist(q.double(), c.double(), compute_mode="donot_use_mm_for_euclid_dist"))
+    oracle_off = float((oracle.double() - truth).abs().max())
+    if oracle_off > 2e-6:
+        print(f"CPU ORACLE DISAGREES WITH FLOAT64 by {oracle_off:.3e} (euclid_score, dense)")
+    torch.testing.assert_close(got.double(), truth, rtol=0, atol=2e-6)
+    torch.testing.assert_close(got, oracle, rtol=0, atol=max(2e-6, 2 * oracle_off))
+
+
 ARBITRATIONS = []   # every time the float64 arbitration below let a run continue (euclid_score only)
 
 
@@ -48,8 +60,9 @@ def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=Non
     want_val = want_val / scale
     if truth is not None and truth[2] == "euclid_score" and not torch.allclose(got_val, want_val, rtol=0, atol=2e-6):
         # If OUR values are off, fail with the evidence; if ours agree with float64 and the oracle's do
-        # not (seen twice in ~100 runs on the GPU boxes' hosts), say so loudly, record it, and go on
-        # with the float64 scores of the oracle's own ranking.
+        # not (it depends on the host CPU's matmul path: a few of the GPU boxes' hosts are off by up to
+        # 3e-5, enough to reorder neighbours), say so loudly, record it, and go on with the ranking the
+        # DEFINITION gives in float64 for those rows.
         q, c, score = truth
         rows = ((got_val - want_val).abs() > 2e-6).any(dim=1).nonzero().flatten()
         t_got = _fp64_scores(q[rows], c, got_idx[rows], score)
@@ -64,8 +77,10 @@ def assert_same_ranking(got_idx, got_val, want_idx, want_val, what="", truth=Non
         warnings.warn("CPU ORACLE DISAGREES WITH FLOAT64 (ours agrees): " + report)
         print("CPU ORACLE DISAGREES WITH FLOAT64 (ours agrees): " + report)
         ARBITRATIONS.append(report)
-        want_val = want_val.clone()
-        want_val[rows] = t_want.float()
+        d64 = torch.cdist(q[rows].double(), c.double(), compute_mode="donot_use_mm_for_euclid_dist")
+        v64, i64 = (1 / (1 + d64)).topk(want_idx.shape[1], dim=1)
+        want_val, want_idx = want_val.clone(), want_idx.clone()
+        want_val[rows], want_idx[rows] = v64.float(), i64
     torch.testing.assert_close(got_val, want_val, rtol=0, atol=2e-6, msg=lambda m: f"{what} scores: {m}")
     mism = (got_idx != want_idx)
     if not mism.any():
@@ -134,7 +149,6 @@ def test_topk_matches_oracle(Q, N, D, k, score, ctas):
     assert_same_ranking(res.indices, res.values, want_idx, want_val, f"{score} {Q}x{N}x{D} k={k}",
                         truth=(q, c, score), scale=scale)
     assert bool((res.margin > 0).all()), "every query must end certified (after the exact re-scan if needed)"
-    assert len(ARBITRATIONS) <= 2, "the float64 arbitration is meant for a rare host-side cdist inaccuracy"
 
 
 def test_topk_large_k_and_small_corpus():
@@ -399,7 +413,7 @@ def test_euclidean_score_operands_and_script_default_score_set():
     want = 2 * (q.bfloat16().float() @ c.bfloat16().float().T) - (c * c).sum(1)[None, :]
     torch.testing.assert_close(keys, want, rtol=0, atol=2e-3 * float(want.abs().max()) / 100)
     dense = qst_b200.euclidean_score(q.to(_dev()), c.to(_dev()))
-    torch.testing.assert_close(dense.cpu(), ir_oracle.euclidean_score(q, c), rtol=0, atol=2e-6)
+    assert_euclid_dense_close(dense.cpu(), q, c, ir_oracle.euclidean_score(q, c))
     # evaluator with the three score functions of the reference script
     qq, cc, queries, corpus, relevant = qst_b200.synth.ir_eval_set(200, 3000, 64)
     table = torch.cat([qq, cc])
@@ -691,7 +705,10 @@ def test_score_functions_called_directly_return_the_dense_matrix(score):
     want = ref(q, c)
     scale = float(want.abs().max()) if score == "dot_score" else 1.0
     assert got.shape == (37, 3001)
-    torch.testing.assert_close(got.cpu() / scale, want / scale, rtol=0, atol=1.2e-5 if score == "euclid_score" else 2e-6)
+    if score == "euclid_score":
+        assert_euclid_dense_close(got.cpu(), q, c, want)
+    else:
+        torch.testing.assert_close(got.cpu() / scale, want / scale, rtol=0, atol=2e-6)
     # 1-D inputs are promoted like the reference does, and the values are the ones topk() emits
     one = fn(q[0].to(_dev()), c.to(_dev()))
     assert one.shape == (1, 3001) and torch.equal(one[0], got[0])
@@ -795,3 +812,26 @@ def test_no_queries_and_non_contiguous_inputs():
     want_val, want_idx = _oracle_topk(qh.float(), c, 10)
     res = qst_b200.topk(qh.to(_dev()), index, 10)
     assert_same_ranking(res.indices, res.values, want_idx, want_val, "fp16 queries")
+
+
+def test_euclid_arbitration_survives_an_inaccurate_host_oracle():
+    """The yardstick logic itself: a CPU oracle whose euclid scores are off by ~2e-5 (what a few hosts'
+    cdist does) reorders neighbours; the float64 arbitration must accept OUR ranking then -- and must
+    still reject a result of ours that is wrong."""
+    import qst_b200
+    g = torch.Generator().manual_seed(8)
+    q = torch.randn(50, 96, generator=g)
+    c = torch.randn(20000, 96, generator=g) * (1 + torch.rand(20000, 1, generator=g))
+    k = 50
+    res = qst_b200.topk(q.to(_dev()), qst_b200.CorpusIndex(c.to(_dev()), "euclid_score"), k)
+    dense = 1 / (1 + torch.cdist(q, c, compute_mode="donot_use_mm_for_euclid_dist"))
+    noisy = dense + 2e-5 * torch.randn(dense.shape, generator=g)
+    bad_val, bad_idx = noisy.topk(k, dim=1)
+    ARBITRATIONS.clear()
+    assert_same_ranking(res.indices, res.values, bad_idx, bad_val, "noisy oracle", truth=(q, c, "euclid_score"))
+    assert len(ARBITRATIONS) == 1
+    wrong = res.values.clone()
+    wrong[3, 7] += 1e-4
+    with pytest.raises(AssertionError):
+        assert_same_ranking(res.indices, wrong, bad_idx, bad_val, "noisy oracle, wrong result", truth=(q, c, "euclid_score"))
+    ARBITRATIONS.clear()

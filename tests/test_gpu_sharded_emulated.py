@@ -163,3 +163,79 @@ def test_sharded_all_zero_query_and_duplicated_documents(master):
         assert bool((m > 0).all()), f"{master} rank {rank}: {m}"
         assert i[4].tolist() == list(range(k)), "all scores tie at 0: the k lowest positions, in order"
         assert i[5, :3].tolist() == [299, 300, 650]
+
+
+@pytest.mark.parametrize("exact", [True, "deferred"])
+def test_prefetched_batches_give_the_same_rankings(exact):
+    """``topk_owned(..., prefetch=next)``: K1 and the distribution of the next batch happen during the
+    current call; the next call starts from the gathered buffers.  A stream of three batches, then a
+    prefetched batch that is NOT the next one asked for (discarded)."""
+    import qst_b200
+    from qst_b200 import comm, sharded
+    g = torch.Generator().manual_seed(21)
+    N, D, k, G, q_own = 20011, 96, 20, 3, 30
+    c = torch.randn(N, D, generator=g)
+    batches = [torch.randn(G * q_own, D, generator=g) for _ in range(4)]
+    want = [_oracle_topk(b, c, k, "cos_sim") for b in batches]
+    dev = _dev()
+    c_dev = c.to(dev)
+    b_dev = [b.to(dev) for b in batches]
+
+    def body(cm):
+        s, e = sharded.shard_bounds(N, cm.world, cm.rank)
+        corp = sharded.ShardedCorpus(c_dev[s:e], N, "cos_sim", comm=cm)
+        own = [b[cm.rank * q_own:(cm.rank + 1) * q_own] for b in b_dev]
+        out = []
+        out.append(corp.topk_owned(own[0], k, exact=exact, prefetch=own[1]))
+        used = corp._prefetched is not None
+        out.append(corp.topk_owned(own[1], k, exact=exact, prefetch=own[2]))
+        out.append(corp.topk_owned(own[2], k, exact=exact, prefetch=own[0]))     # announced: batch 0 ...
+        out.append(corp.topk_owned(own[3], k, exact=exact))                       # ... asked for: batch 3
+        corp.finish_exact()
+        torch.cuda.synchronize()
+        return [(v.cpu(), i.cpu(), m.cpu()) for v, i, m in out], used
+
+    res = comm.run_local_world(G, body)
+    for rank, (out, used) in enumerate(res):
+        assert used, "peer-mapped buffers exist on an emulated node: the prefetch path must have been taken"
+        for b, (v, i, m) in enumerate(out):
+            lo, hi = rank * q_own, (rank + 1) * q_own
+            assert_same_ranking(i, v, want[b][1][lo:hi], want[b][0][lo:hi], f"batch {b} rank {rank} exact={exact}")
+            assert bool((m > 0).all())
+
+
+@pytest.mark.parametrize("lookahead", [False, True])
+def test_sharded_host_pipeline_with_and_without_lookahead(lookahead):
+    """``ShardedHostPipeline``: pinned host slices in, pinned rankings out, double-buffered; with
+    ``submit(cur, next)`` the next batch is copied in and distributed one step ahead."""
+    import qst_b200
+    from qst_b200 import comm, sharded
+    g = torch.Generator().manual_seed(33)
+    N, D, k, G, q_own = 15013, 64, 10, 2, 40
+    c = torch.randn(N, D, generator=g)
+    batches = [torch.randn(G * q_own, D, generator=g) for _ in range(5)]
+    want = [_oracle_topk(b, c, k, "cos_sim") for b in batches]
+    c_dev = c.to(_dev())
+
+    def body(cm):
+        s, e = sharded.shard_bounds(N, cm.world, cm.rank)
+        corp = sharded.ShardedCorpus(c_dev[s:e], N, "cos_sim", comm=cm)
+        own = [b[cm.rank * q_own:(cm.rank + 1) * q_own].contiguous().pin_memory() for b in batches]
+        pipe = sharded.ShardedHostPipeline(corp, k)
+        out, tickets = [], []
+        for t in range(len(own)):
+            nxt = own[t + 1] if (lookahead and t + 1 < len(own)) else None
+            tickets.append(pipe.submit(own[t], nxt) if nxt is not None else pipe.submit(own[t]))
+            if t >= 1:
+                v, i = pipe.result(tickets[t - 1])
+                out.append((v.clone(), i.clone()))
+        v, i = pipe.result(tickets[-1])
+        out.append((v.clone(), i.clone()))
+        pipe.drain()
+        return out
+
+    res = comm.run_local_world(G, body)
+    for rank, out in enumerate(res):
+        lo, hi = rank * q_own, (rank + 1) * q_own
+        for b, (v, i) in enumerate(out):
+            assert_same_ranking(i, v, want[b][1][lo:hi], want[b][0][lo:hi], f"pipeline batch {b} rank {rank}")
