@@ -200,6 +200,7 @@ int qst_score_select(const qst_topk_plan* plan, const void* q_bf16, const void* 
  * the launch (and keeps two generations so a fast rank never pushes into a buffer being cleared).
  * Purely opportunistic: no rank ever waits on another inside the kernel. */
 #define QST_MAX_PEERS 15
+#define QST_MAX_WORLD (QST_MAX_PEERS + 1)
 #define QST_IPC_HANDLE_BYTES 64
 int qst_score_select_peers(const qst_topk_plan* plan, const void* q_bf16, const void* c_bf16, void* workspace,
                            void* hint_local, void* const* peer_hints, int n_peers, qst_stream_t stream);
@@ -297,6 +298,40 @@ int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t n_total, co
 int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
                          const float* q_inv, const float* c_f32, const float* c_inv, float* out,
                          qst_stream_t stream);
+
+/* ---- the three exchanges of the sharded path FUSED into their producer kernels over peer memory.
+ * Each exchange is "rows grouped in G blocks of rows_per_block rows, block b is meant for rank b"
+ * (candidate lists -> owners, requests -> shards, exact scores -> owners).  With a qst_scatter the
+ * producing kernel stores every finished row straight into rank b's receive buffer (a peer-mapped
+ * buffer from qst_peer_buffer_create / _open, base[b]; base[rank] is the caller's own) at row
+ * (rank * rows_per_block + i) -- whole rows, coalesced, over NVLink while the kernel is still
+ * producing the next ones -- and the all-to-all that followed it (qst_comm_alltoall, i.e. what replaces
+ * the sequential chunk loop of ir_evauation_script.py:161) shrinks to qst_peer_barrier: every rank signals
+ * every rank's flag word (release, system scope) and waits for all of theirs.  `flags` reuses the
+ * descriptor: base[r] = rank r's flag array (QST_MAX_WORLD uint32, zeroed once), rows_per_block ignored;
+ * `epoch` must grow by one per barrier, identically on all ranks.  The receive layout is exactly what the
+ * all-to-all would have delivered, so the consumers (qst_select_requests, qst_rescore_requests,
+ * qst_finalize_exact) are unchanged.  A rank that never arrives makes the barrier trap after 120 s
+ * (environment QST_BARRIER_TIMEOUT_S) instead of hanging the GPU.
+ *   qst_select_candidates_scatter : as qst_select_candidates, lists go to dst (G * rows_per_block = plan->Q)
+ *   qst_select_requests_scatter   : as qst_select_requests; out_req is still written locally
+ *                                   (qst_finalize_exact reads it) and block g also goes to shard g
+ *   qst_rescore_requests_scatter  : as qst_rescore_requests; `staging` [rows, m] fp32 is scratch */
+typedef struct qst_scatter {
+  void* base[QST_MAX_WORLD];
+  int32_t world, rank;
+  int64_t rows_per_block;
+} qst_scatter;
+int qst_select_candidates_scatter(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
+                                  const qst_scatter* dst, qst_stream_t stream);
+int qst_select_requests_scatter(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
+                                int32_t* out_req, uint32_t* out_bound, void* scratch, const qst_scatter* dst,
+                                qst_stream_t stream);
+int qst_rescore_requests_scatter(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
+                                 const float* q_inv, const float* c_f32, const float* c_inv, float* staging,
+                                 const qst_scatter* dst, qst_stream_t stream);
+int qst_peer_barrier(const qst_scatter* flags, uint32_t epoch, qst_stream_t stream);
+
 int qst_finalize_exact(int64_t Q, int G, int m, int k, int score, int64_t D, int64_t n_total,
                        const int32_t* req, const float* exact, const uint32_t* bound, const float* q_f32,
                        const float* q_err, const float* c_stats, float* out_val, int64_t* out_idx,

@@ -46,6 +46,15 @@ class TopkPlan(C.Structure):
                 ("off_cand", C.c_size_t), ("qs", C.c_int32), ("reserved_", C.c_int32)]
 
 
+QST_MAX_WORLD = 16
+
+
+class Scatter(C.Structure):
+    """``qst_scatter`` of include/qst.h: peer-mapped receive buffers of the ranks of a node."""
+    _fields_ = [("base", C.c_void_p * QST_MAX_WORLD), ("world", C.c_int32), ("rank", C.c_int32),
+                ("rows_per_block", C.c_int64)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _INT = C.c_int
@@ -87,6 +96,10 @@ SIGNATURES = {
                                   _P, _P]),
     "qst_select_requests": (_INT, [_I64, _INT, _INT, _INT, _I64, _P, _P, _P, _P, _P]),
     "qst_rescore_requests": (_INT, [_I64, _INT, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),
+    "qst_select_candidates_scatter": (_INT, [C.POINTER(TopkPlan), _P, _INT, _I64, C.POINTER(Scatter), _P]),
+    "qst_select_requests_scatter": (_INT, [_I64, _INT, _INT, _INT, _I64, _P, _P, _P, _P, C.POINTER(Scatter), _P]),
+    "qst_rescore_requests_scatter": (_INT, [_I64, _INT, _I64, _INT, _P, _P, _P, _P, _P, _P, C.POINTER(Scatter), _P]),
+    "qst_peer_barrier": (_INT, [C.POINTER(Scatter), C.c_uint32, _P]),
     "qst_finalize_exact": (_INT, [_I64, _INT, _INT, _INT, _INT, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "qst_exact_rescan_lists": (_INT, [_I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "qst_exact_rescan_workspace_bytes": (C.c_size_t, [_I64, _INT]),

@@ -61,6 +61,22 @@ class Comm:
         """Collective.  None when peer-writable memory is not available (the caller then does without)."""
         return None
 
+    def scatter_descriptor(self, buffers: SharedBuffers, offset: int, rows_per_block: int) -> "_lib.Scatter":
+        """``qst_scatter`` over `buffers` (+ byte offset) of every rank, in rank order."""
+        sc = _lib.Scatter()
+        others = iter(buffers.peers)
+        for r in range(self.world):
+            sc.base[r] = (buffers.local if r == self.rank else next(others)) + offset
+        sc.world, sc.rank, sc.rows_per_block = self.world, self.rank, rows_per_block
+        return sc
+
+    def peer_barrier(self, flags: "_lib.Scatter", epoch: int, device: torch.device) -> None:
+        """Barrier of the node's ranks over peer memory, ordered on the current stream
+        (``qst_peer_barrier``): everything a rank's stream wrote before it -- into ANY rank's buffers --
+        is visible to every rank's stream after it."""
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().qst_peer_barrier(C.byref(flags), epoch, torch.cuda.current_stream(device).cuda_stream))
+
 
 class SingleComm(Comm):
     """World of one: every collective is the identity."""
@@ -265,6 +281,12 @@ class LocalComm(Comm):
         return self._exchange(t, lambda got: torch.stack(got).amax(dim=0))
 
     def barrier(self):
+        self._w.barrier.wait()
+
+    def peer_barrier(self, flags, epoch, device):
+        # the "ranks" share one device (and often one stream): a spinning kernel would wait for work
+        # queued behind it -- drain this thread's stream and meet on the host instead
+        torch.cuda.current_stream(device).synchronize()
         self._w.barrier.wait()
 
     def shared_buffers(self, nbytes, device):

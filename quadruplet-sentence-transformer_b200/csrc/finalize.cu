@@ -167,6 +167,25 @@ __device__ __forceinline__ float apply_score(float dot, int score, float q_inv, 
   return score == QST_SCORE_COS ? (dot * q_inv) * (c_inv ? c_inv[row] : 1.0f) : dot;
 }
 
+// Destination of a producer kernel of the sharded path whose output rows are grouped in `world` blocks of
+// `rows_per_block` rows, block b being meant for rank b (candidate lists -> owners, requests -> shards,
+// exact scores -> owners).  world == 0: plain local output.  Otherwise row (b, i) is stored at row
+// (rank * rows_per_block + i) of base[b] -- rank b's peer-mapped receive buffer, written straight over
+// NVLink by the kernel that produces the row (the all-to-all that would follow is a flag barrier).
+struct Scatter {
+  void* base[QST_MAX_WORLD];
+  int world, rank;
+  long long rows_per_block;
+};
+
+template <typename T>
+__device__ __forceinline__ T* scatter_row(const Scatter& sc, T* local, long long row, long long pitch) {
+  if (sc.world == 0) return local + row * pitch;
+  const long long b = row / sc.rows_per_block;
+  const long long i = row - b * sc.rows_per_block;
+  return reinterpret_cast<T*>(sc.base[b]) + ((long long)sc.rank * sc.rows_per_block + i) * pitch;
+}
+
 struct FinParams {
   int Q, N, D;
   int k, kprime, cap, m_tiles, stripes, score, rows_per_unit;
@@ -183,6 +202,7 @@ struct FinParams {
   // select-only mode (sharded retrieval, step 1): write the m best candidates by bf16 key instead
   // of rescoring; entry m of each row carries (bound key, count)
   uint2* sel_out;
+  Scatter scat;   // where sel_out / req_out rows go when the exchange is fused into this kernel
   // request mode (fully sharded master, owner side): instead of rescoring, the k' best candidates are
   // grouped by the shard that holds them: req_out [G, Q, req_m] local row ids (-1 = none),
   // bound_out [Q] = bf16 key bounding everything that is NOT requested
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
   if (P.sel_out) {
     // everything this shard did not put in the list has a bf16 key <= bound
     const uint32_t bound = reduced ? max(T, Tstar) : Tstar;
-    uint2* dst = P.sel_out + (size_t)q * (P.kprime + 1);
+    uint2* dst = scatter_row(P.scat, P.sel_out, q, P.kprime + 1);
     for (int i = tid; i < P.kprime; i += kFinThreads)
       dst[i] = i < ncand ? make_uint2(keys[i], (uint32_t)((int64_t)idx[i] + P.idx_offset)) : make_uint2(0u, 0xffffffffu);
     if (tid == 0) dst[P.kprime] = make_uint2(bound, (uint32_t)ncand);
@@ -328,6 +348,16 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinParams P
       if (slot < P.req_m) P.req_out[((size_t)g * P.Q + q) * P.req_m + slot] = (int32_t)(id - start);
     }
     if (tid == 0) P.bound_out[q] = reduced ? max(T, Tstar) : Tstar;
+    if (P.scat.world) {
+      // the rows just written (scattered 4-byte stores, kept: finalize_exact reads them) go to their
+      // shards as whole rows, coalesced, straight into the shard's receive buffer
+      __syncthreads();
+      for (int g = 0; g < P.req_G; ++g) {
+        const int32_t* src = P.req_out + ((size_t)g * P.Q + q) * P.req_m;
+        int32_t* dst = scatter_row(P.scat, static_cast<int32_t*>(nullptr), (long long)g * P.Q + q, P.req_m);
+        for (int j = tid; j < P.req_m; j += kFinThreads) dst[j] = __ldcg(src + j);
+      }
+    }
     return;
   }
   // every document that is NOT rescored below has a bf16 score <= t_bf
@@ -611,7 +641,8 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_kernel(int m, in
                                                                        const float* __restrict__ q_f32,
                                                                        const float* __restrict__ q_inv,
                                                                        const float* __restrict__ c_f32,
-                                                                       const float* __restrict__ c_inv, float* __restrict__ out) {
+                                                                       const float* __restrict__ c_inv, float* __restrict__ out,
+                                                                       const Scatter scat) {
   extern __shared__ float rq_row[];
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -653,6 +684,11 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_kernel(int m, in
       }
     }
   }
+  if (scat.world) {   // the finished row goes to the owner of the query, coalesced (see Scatter)
+    __syncthreads();
+    float* dst = scatter_row(scat, static_cast<float*>(nullptr), q, m);
+    for (int j = tid; j < m; j += kFinThreads) dst[j] = __ldcg(o + j);
+  }
 }
 
 // Same work, ONE WARP per (owner, query) row with the query row held in registers (D <= 1024, D % 4 == 0):
@@ -669,7 +705,7 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_warp_kernel(int6
                                                                             const float* __restrict__ q_inv,
                                                                             const float* __restrict__ c_f32,
                                                                             const float* __restrict__ c_inv,
-                                                                            float* __restrict__ out) {
+                                                                            float* __restrict__ out, const Scatter scat) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
   if (q >= rows) return;
@@ -683,11 +719,11 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_warp_kernel(int6
   }
   const float qi = (score == QST_SCORE_COS && q_inv) ? q_inv[q] : 1.0f;
   const int32_t* rq = req + (size_t)q * m;
-  float* o = out + (size_t)q * m;
+  float* o = scatter_row(scat, out, q, m);   // local row, or the row in the query owner's receive buffer
   for (int j0 = 0; j0 < m; j0 += 32) {
     const int jj = j0 + lane;
     const int my = jj < m ? rq[jj] : -1;
-    if (jj < m && my < 0) o[jj] = -INFINITY;
+    float res = -INFINITY;                   // lane j keeps the score of entry j0 + j: one coalesced store per 32
     unsigned valid = __ballot_sync(0xffffffffu, my >= 0);
     while (valid) {
       // two requested rows per trip: twice the loads in flight
@@ -713,11 +749,10 @@ __global__ void __launch_bounds__(kFinThreads) rescore_requests_warp_kernel(int6
       }
       a0 = warp_sum(a0);
       a1 = warp_sum(a1);
-      if (lane == 0) {
-        o[j0 + l0] = SQ ? a0 : apply_score(a0, score, qi, c_inv, r0);
-        if (l1 >= 0) o[j0 + l1] = SQ ? a1 : apply_score(a1, score, qi, c_inv, r1);
-      }
+      if (lane == l0) res = SQ ? a0 : apply_score(a0, score, qi, c_inv, r0);
+      if (lane == l1) res = SQ ? a1 : apply_score(a1, score, qi, c_inv, r1);
     }
+    if (jj < m) o[jj] = res;
   }
 }
 
@@ -879,7 +914,7 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_rows_warp_kernel(const 
     reduced = true;
   }
   __syncwarp();
-  uint2* dst = P.sel_out + (size_t)q * (m + 1);
+  uint2* dst = scatter_row(P.scat, P.sel_out, q, m + 1);
   for (int i = lane; i < m; i += 32) {
     uint2 e = make_uint2(0u, 0xffffffffu);
     if (i < fill) { e = win[i]; e.y = (uint32_t)((int64_t)(int32_t)e.y + P.idx_offset); }
@@ -896,9 +931,63 @@ __global__ void unpack_list_trailers_kernel(const uint2* __restrict__ lists, int
   cnt[i] = (int)t.y;
 }
 
+// Barrier over peer memory between the ranks of a node, stream-ordered: thread t signals rank t
+// (release at system scope: everything this stream wrote before, peer writes included, is visible to
+// whoever sees the flag) and waits for rank t's signal in the local flag array.  Epochs only grow, so a
+// rank that is already one barrier ahead cannot be missed.  A rank that never arrives (crashed peer) would
+// hang the GPU: after `timeout_ns` (120 s unless QST_BARRIER_TIMEOUT_S says otherwise) the kernel traps instead.
+__global__ void peer_barrier_kernel(const Scatter flags, uint32_t epoch, unsigned long long timeout_ns) {
+  const int t = threadIdx.x;
+  if (t >= flags.world) return;
+  __threadfence_system();
+  uint32_t* remote = reinterpret_cast<uint32_t*>(flags.base[t]) + flags.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.base[flags.rank]) + t;
+  unsigned long long t0 = 0, now = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - t0 > timeout_ns) __trap();
+    __nanosleep(200);
+  }
+}
+
 }  // namespace qst
 
 using namespace qst;
+
+static int scatter_from(const qst_scatter* dst, Scatter* out) {
+  *out = Scatter{};
+  if (dst == nullptr) return QST_OK;
+  QST_CHECK_ARG(dst->world >= 1 && dst->world <= QST_MAX_WORLD && dst->rank >= 0 && dst->rank < dst->world &&
+                    dst->rows_per_block >= 1,
+                "scatter: bad descriptor world=%d rank=%d rows_per_block=%lld", dst->world, dst->rank,
+                (long long)dst->rows_per_block);
+  for (int r = 0; r < dst->world; ++r) {
+    QST_CHECK_ARG(dst->base[r] != nullptr, "scatter: null base pointer for rank %d", r);
+    out->base[r] = dst->base[r];
+  }
+  out->world = dst->world; out->rank = dst->rank; out->rows_per_block = dst->rows_per_block;
+  return QST_OK;
+}
+
+extern "C" int qst_peer_barrier(const qst_scatter* flags, uint32_t epoch, qst_stream_t stream) {
+  QST_CHECK_ARG(flags != nullptr, "peer_barrier: null descriptor");
+  Scatter f;
+  if (int rc = scatter_from(flags, &f)) return rc;
+  static unsigned long long timeout_ns = 0;
+  if (timeout_ns == 0) {
+    const char* e = getenv("QST_BARRIER_TIMEOUT_S");
+    const double sec = e ? atof(e) : 120.0;
+    timeout_ns = (unsigned long long)((sec > 0.001 ? sec : 120.0) * 1e9);
+  }
+  peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(f, epoch, timeout_ns);
+  QST_LAUNCH_CHECK();
+  return QST_OK;
+}
 
 static int finalize_topk_impl(const qst_topk_plan* plan, int kprime, int refine, const void* workspace, const float* q_f32,
                               const float* q_inv, const float* q_err, const float* c_f32, const float* c_inv,
@@ -971,10 +1060,12 @@ static int finalize_topk_impl(const qst_topk_plan* plan, int kprime, int refine,
   return QST_OK;
 }
 
-extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
-                                     void* out_lists, qst_stream_t stream) {
-  QST_CHECK_ARG(plan && workspace && out_lists, "select_candidates: null argument");
+static int select_candidates_impl(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
+                                  void* out_lists, const qst_scatter* dst, qst_stream_t stream) {
+  QST_CHECK_ARG(plan && workspace && (out_lists || dst), "select_candidates: null argument");
   QST_CHECK_ARG(m >= 1 && m <= 2048, "select_candidates: m=%d out of range", m);
+  QST_CHECK_ARG(!dst || (int64_t)dst->world * dst->rows_per_block == plan->Q,
+                "select_candidates: scatter blocks do not cover the %lld query rows", (long long)plan->Q);
   QST_CHECK_ARG(plan->stripes <= kMaxStripes, "select_candidates: too many stripes (%d)", plan->stripes);
   const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
   FinParams P{};
@@ -993,6 +1084,8 @@ extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* work
   P.unit_cand = reinterpret_cast<const uint2*>(ws + plan->off_cand);
   P.idx_offset = idx_offset;
   P.sel_out = reinterpret_cast<uint2*>(out_lists);
+  if (int rc = scatter_from(dst, &P.scat)) return rc;
+  if (dst && !P.sel_out) P.sel_out = reinterpret_cast<uint2*>(dst->base[dst->rank]);   // marks the mode only
   {
     const char* e = getenv("QST_SELECT_CTA");   // 1 forces the CTA-per-row kernel (comparison / debugging)
     if (m <= kSelWarpWindow / 2 && !(e && e[0] == '1')) {
@@ -1007,6 +1100,18 @@ extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* work
   finalize_kernel<<<(unsigned)plan->Q, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
   QST_LAUNCH_CHECK();
   return QST_OK;
+}
+
+extern "C" int qst_select_candidates(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
+                                     void* out_lists, qst_stream_t stream) {
+  QST_CHECK_ARG(out_lists != nullptr, "select_candidates: null output");
+  return select_candidates_impl(plan, workspace, m, idx_offset, out_lists, nullptr, stream);
+}
+
+extern "C" int qst_select_candidates_scatter(const qst_topk_plan* plan, const void* workspace, int m, int64_t idx_offset,
+                                             const qst_scatter* dst, qst_stream_t stream) {
+  QST_CHECK_ARG(dst != nullptr, "select_candidates_scatter: null descriptor");
+  return select_candidates_impl(plan, workspace, m, idx_offset, nullptr, dst, stream);
 }
 
 extern "C" int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, int score, int64_t D,
@@ -1046,9 +1151,12 @@ extern "C" int qst_finalize_lists(int64_t Q, int G, int m, int k, int kprime, in
 
 extern "C" size_t qst_finalize_lists_scratch_bytes(int64_t Q, int G) { return (size_t)G * Q * 8; }
 
-extern "C" int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
-                                   int32_t* out_req, uint32_t* out_bound, void* scratch, qst_stream_t stream) {
+static int select_requests_impl(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
+                                int32_t* out_req, uint32_t* out_bound, void* scratch, const qst_scatter* dst,
+                                qst_stream_t stream) {
   QST_CHECK_ARG(lists && out_req && out_bound && scratch, "select_requests: null argument");
+  QST_CHECK_ARG(!dst || (dst->world == G && dst->rows_per_block == Q),
+                "select_requests: scatter descriptor must have one block of Q rows per shard");
   QST_CHECK_ARG(Q >= 1 && G >= 1 && G <= kMaxStripes && m >= 1 && kprime >= 1 && kprime <= 2048 && n_total >= G,
                 "select_requests: bad shape Q=%lld G=%d m=%d kprime=%d n_total=%lld", (long long)Q, G, m, kprime,
                 (long long)n_total);
@@ -1070,6 +1178,7 @@ extern "C" int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t 
   P.sm_cap = sm_cap;
   P.unit_cnt = cnt; P.unit_thr = thr; P.unit_cand = reinterpret_cast<const uint2*>(lists);
   P.req_out = out_req; P.bound_out = out_bound; P.req_G = G; P.req_m = m; P.n_total = n_total;
+  if (int rc = scatter_from(dst, &P.scat)) return rc;
   const size_t smem = (size_t)sm_cap * 8 + (size_t)kprime * 8 + 16;
   QST_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   finalize_kernel<<<(unsigned)Q, kFinThreads, smem, st>>>(P);
@@ -1077,10 +1186,26 @@ extern "C" int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t 
   return QST_OK;
 }
 
-extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
-                                    const float* q_inv, const float* c_f32, const float* c_inv, float* out,
-                                    qst_stream_t stream) {
+extern "C" int qst_select_requests(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
+                                   int32_t* out_req, uint32_t* out_bound, void* scratch, qst_stream_t stream) {
+  return select_requests_impl(Q, G, m, kprime, n_total, lists, out_req, out_bound, scratch, nullptr, stream);
+}
+
+extern "C" int qst_select_requests_scatter(int64_t Q, int G, int m, int kprime, int64_t n_total, const void* lists,
+                                           int32_t* out_req, uint32_t* out_bound, void* scratch,
+                                           const qst_scatter* dst, qst_stream_t stream) {
+  QST_CHECK_ARG(dst != nullptr, "select_requests_scatter: null descriptor");
+  return select_requests_impl(Q, G, m, kprime, n_total, lists, out_req, out_bound, scratch, dst, stream);
+}
+
+static int rescore_requests_impl(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
+                                 const float* q_inv, const float* c_f32, const float* c_inv, float* out,
+                                 const qst_scatter* dst, qst_stream_t stream) {
   QST_CHECK_ARG(req && q_f32 && c_f32 && out, "rescore_requests: null argument");
+  QST_CHECK_ARG(!dst || (int64_t)dst->world * dst->rows_per_block == rows,
+                "rescore_requests: scatter blocks do not cover the %lld rows", (long long)rows);
+  Scatter scat;
+  if (int rc = scatter_from(dst, &scat)) return rc;
   QST_CHECK_ARG(rows >= 1 && m >= 1 && D >= 1 && D * 4 <= 200 * 1024, "rescore_requests: bad shape rows=%lld m=%d D=%lld",
                 (long long)rows, m, (long long)D);
   QST_CHECK_ARG(score >= QST_SCORE_COS && score <= QST_SCORE_EUCLID, "rescore_requests: unknown score %d", score);
@@ -1092,9 +1217,9 @@ extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, c
       const unsigned grid = (unsigned)ceil_div(rows, kFinWarps);
       cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
       if (score == QST_SCORE_EUCLID)
-        rescore_requests_warp_kernel<true><<<grid, kFinThreads, 0, st>>>(rows, m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+        rescore_requests_warp_kernel<true><<<grid, kFinThreads, 0, st>>>(rows, m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out, scat);
       else
-        rescore_requests_warp_kernel<false><<<grid, kFinThreads, 0, st>>>(rows, m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+        rescore_requests_warp_kernel<false><<<grid, kFinThreads, 0, st>>>(rows, m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out, scat);
       QST_LAUNCH_CHECK();
       return QST_OK;
     }
@@ -1102,9 +1227,23 @@ extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, c
   const size_t smem = round_up((size_t)D * 4, 16);
   QST_CUDA(cudaFuncSetAttribute(rescore_requests_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rescore_requests_kernel<<<(unsigned)rows, kFinThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out);
+      m, (int)D, score, req, q_f32, q_inv, c_f32, c_inv, out, scat);
   QST_LAUNCH_CHECK();
   return QST_OK;
+}
+
+extern "C" int qst_rescore_requests(int64_t rows, int m, int64_t D, int score, const int32_t* req, const float* q_f32,
+                                    const float* q_inv, const float* c_f32, const float* c_inv, float* out,
+                                    qst_stream_t stream) {
+  return rescore_requests_impl(rows, m, D, score, req, q_f32, q_inv, c_f32, c_inv, out, nullptr, stream);
+}
+
+extern "C" int qst_rescore_requests_scatter(int64_t rows, int m, int64_t D, int score, const int32_t* req,
+                                            const float* q_f32, const float* q_inv, const float* c_f32,
+                                            const float* c_inv, float* staging, const qst_scatter* dst,
+                                            qst_stream_t stream) {
+  QST_CHECK_ARG(dst != nullptr, "rescore_requests_scatter: null descriptor");
+  return rescore_requests_impl(rows, m, D, score, req, q_f32, q_inv, c_f32, c_inv, staging, dst, stream);
 }
 
 extern "C" int qst_dense_scores(int64_t Q, int64_t N, int64_t D, int score, const float* q_f32, const float* q_inv,

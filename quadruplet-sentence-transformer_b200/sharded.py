@@ -195,6 +195,56 @@ class PeerGather:
             self.buffers = None
 
 
+class ExchangeArena:
+    """Receive buffers of the three exchanges of the sharded step (candidate lists -> owners, requests ->
+    shards, exact scores -> owners), peer-mapped, two generations, plus the flag words of the barrier.
+
+    With it the exchanges are FUSED into their producer kernels: ``qst_select_candidates_scatter``,
+    ``qst_select_requests_scatter`` and ``qst_rescore_requests_scatter`` store every finished row straight
+    into the receiving rank's buffer over NVLink, and what is left of each all-to-all is
+    ``qst_peer_barrier`` (every rank signals every rank, release/acquire at system scope).  The receive
+    layout is the one the all-to-all would have produced.  Generation g serves step g mod 2: a rank can be
+    at most one barrier ahead of another, and a region written in step i was last read in step i-2."""
+
+    LISTS, REQ, EXACT = 0, 1, 2
+
+    def __init__(self, q_own: int, m: int, comm: Comm, device: torch.device):
+        G = comm.world
+        self.q_own, self.m, self.comm, self.device = q_own, m, comm, device
+        sizes = (G * q_own * (m + 1) * 8, G * q_own * m * 4, G * q_own * m * 4)
+        self.off, off = [], 0
+        for b in sizes:
+            self.off.append(off)
+            off += ((b + 255) // 256) * 256
+        self.gen_bytes = off
+        self.buffers = comm.shared_buffers(2 * self.gen_bytes + 256, device) if G <= _lib.QST_MAX_WORLD else None
+        self.ok = self.buffers is not None
+        self.step, self.epoch = 0, 0
+        self._flags = comm.scatter_descriptor(self.buffers, 2 * self.gen_bytes, 1) if self.ok else None
+
+    def _gen(self) -> int:
+        return (self.step % 2) * self.gen_bytes
+
+    def dst(self, region: int):
+        """Scatter descriptor of `region` in the current generation (rows per block: q_own)."""
+        return self.comm.scatter_descriptor(self.buffers, self._gen() + self.off[region], self.q_own)
+
+    def local(self, region: int) -> int:
+        return self.buffers.local + self._gen() + self.off[region]
+
+    def barrier(self):
+        self.epoch += 1
+        self.comm.peer_barrier(self._flags, self.epoch & 0xffffffff, self.device)
+
+    def advance(self):
+        self.step += 1
+
+    def close(self):
+        if self.buffers is not None:
+            self.buffers.close()
+            self.buffers = None
+
+
 class ShardedCorpus:
     """This rank's shard of an N-row corpus + the collective top-k over all shards.
 
@@ -222,6 +272,8 @@ class ShardedCorpus:
         self._peer_hints_off = bool(os.environ.get("QST_NO_PEER_HINTS"))
         self._peer_gather: Optional[PeerGather] = None
         self._peer_gather_off = bool(os.environ.get("QST_NO_PEER_GATHER"))
+        self._arena: Optional[ExchangeArena] = None
+        self._arena_off = bool(os.environ.get("QST_NO_FUSED_EXCHANGE"))
         self._timing = [] if os.environ.get("QST_SHARD_TIMING") else None   # debug: per-stage CUDA events
         self.master = None
         self.last_rescanned = 0      # queries repaired by the distributed exact re-scan in the last call
@@ -245,11 +297,11 @@ class ShardedCorpus:
         self.finish_exact()
         self._prefetched = None
         dev = self.index.device
-        if self._peer_hints is not None or self._peer_gather is not None:
+        if self._peer_hints is not None or self._peer_gather is not None or self._arena is not None:
             torch.cuda.synchronize(dev)
             if self.world > 1:
                 self.comm.barrier()          # nobody may still be writing into a buffer that goes away
-        for holder in ("_peer_hints", "_peer_gather"):
+        for holder in ("_peer_hints", "_peer_gather", "_arena"):
             obj = getattr(self, holder)
             if obj is not None:
                 obj.close()
@@ -326,6 +378,21 @@ class ShardedCorpus:
                 return None
         return self._peer_gather
 
+    def _arena_for(self, q_own: int, m: int, dev) -> Optional[ExchangeArena]:
+        """Peer-mapped receive buffers for the fused exchanges (collective on first use / resize)."""
+        if self._arena_off or self.world == 1:
+            return None
+        if self._arena is None or (self._arena.q_own, self._arena.m) != (q_own, m):
+            if self._arena is not None:
+                torch.cuda.synchronize(dev)
+                self.comm.barrier()
+                self._arena.close()
+            self._arena = ExchangeArena(q_own, m, self.comm, dev)
+            if not self._arena.ok:
+                self._arena_off = True
+                self._arena = None
+        return self._arena
+
     def _mark(self, marks, name):
         if marks is not None:
             e = torch.cuda.Event(enable_timing=True)
@@ -391,9 +458,10 @@ class ShardedCorpus:
             return self._topk_owned_replicated(own_queries, k, kprime, exact)
         return self._topk_owned_sharded(own_queries, k, kprime, exact, prefetch)
 
-    def _select_pass(self, q_bf16, q_pad, k, kprime, marks):
+    def _select_pass(self, q_bf16, q_pad, k, kprime, marks, fused=False):
         """K2 on the local shard for all q_pad queries + the per-query candidate lists by bf16 key.
-        Returns (lists [q_pad, m+1, 2] int32, m, k' of the whole corpus)."""
+        Returns (lists [q_pad, m+1, 2] int32, m, k' of the whole corpus) -- or, with ``fused`` and
+        peer-mapped receive buffers, (the ExchangeArena the lists were scattered into, m, k')."""
         lib = _lib.load()
         dev = self.index.device
         G, score = self.world, self.score
@@ -420,6 +488,13 @@ class ShardedCorpus:
             _lib.check(lib.qst_score_select(C.byref(plan), _lib.ptr(q_bf16), self.index.rows.bf16.data_ptr(),
                                             ws.data_ptr(), st))
         self._mark(marks, "K2")
+        arena = self._arena_for(q_pad // G, m, dev) if fused else None
+        if arena is not None:
+            # every list goes straight into its owner's receive buffer, written by the kernel that makes it
+            dst = arena.dst(ExchangeArena.LISTS)
+            _lib.check(lib.qst_select_candidates_scatter(C.byref(plan), ws.data_ptr(), m, self.start, C.byref(dst), st))
+            self._mark(marks, "select")
+            return arena, m, kprime_all
         lists = torch.empty((q_pad, m + 1, 2), dtype=torch.int32, device=dev)
         _lib.check(lib.qst_select_candidates(C.byref(plan), ws.data_ptr(), m, self.start, lists.data_ptr(), st))
         self._mark(marks, "select")
@@ -502,7 +577,8 @@ class ShardedCorpus:
                 own_f32_ptr, own_err_ptr = pq.f32[own].data_ptr(), pq.err[own].data_ptr()
                 keep = (pq,)
             self._mark(marks, "gather_q+prep")
-            lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks)
+            lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks, fused=G > 1)
+            arena = lists if isinstance(lists, ExchangeArena) else None
             if prefetch is not None:
                 sel_done = torch.cuda.Event()
                 sel_done.record()
@@ -511,30 +587,56 @@ class ShardedCorpus:
                 # this rank's pushes are done before it enters the exchange; the exchange completes only
                 # after every rank has entered it, i.e. after every rank's pushes are done
                 torch.cuda.current_stream(dev).wait_event(pushed)
-            recv = comm.all_to_all(lists) if G > 1 else lists                     # [G, q_own, m+1, 2]
-            self._mark(marks, "all_to_all")
             req = torch.empty((G * q_own, m), dtype=torch.int32, device=dev)      # [G shards, q_own, m]
             bound = torch.empty(q_own, dtype=torch.int32, device=dev)
             scratch = self._ws(lib.qst_finalize_lists_scratch_bytes(q_own, G), "lists")
-            _lib.check(lib.qst_select_requests(q_own, G, m, kprime_all, self.n_total, recv.data_ptr(),
-                                               req.data_ptr(), bound.data_ptr(), scratch.data_ptr(), st))
-            self._mark(marks, "requests")
-            req_in = comm.all_to_all(req) if G > 1 else req                       # [G owners, q_own, m]
             exact_out = torch.empty((G * q_own, m), dtype=torch.float32, device=dev)
             c = self.index.rows
-            _lib.check(lib.qst_rescore_requests(G * q_own, m, D, code, req_in.data_ptr(), q_all_ptr,
-                                                _lib.ptr(q_inv_all), c.f32.data_ptr(),
-                                                c.inv_norm.data_ptr() if cos else None, exact_out.data_ptr(), st))
-            self._mark(marks, "rescore")
-            if prefetch is not None:
-                # the next batch's pushes (started after K2, long done) are published by this exchange
-                torch.cuda.current_stream(dev).wait_event(self._prefetched[4])
-            exact_in = comm.all_to_all(exact_out) if G > 1 else exact_out         # [G shards, q_own, m]
+            if arena is not None:
+                # Exchanges fused into their producers: the rows were / are stored straight into the
+                # receiving rank's buffer by the kernel that makes them; a flag barrier over peer memory
+                # is all that is left of each all-to-all.
+                arena.barrier()                                                   # lists have landed everywhere
+                self._mark(marks, "all_to_all")
+                dst = arena.dst(ExchangeArena.REQ)
+                _lib.check(lib.qst_select_requests_scatter(q_own, G, m, kprime_all, self.n_total,
+                                                           arena.local(ExchangeArena.LISTS), req.data_ptr(),
+                                                           bound.data_ptr(), scratch.data_ptr(), C.byref(dst), st))
+                self._mark(marks, "requests")
+                arena.barrier()                                                   # requests have landed
+                dst = arena.dst(ExchangeArena.EXACT)
+                _lib.check(lib.qst_rescore_requests_scatter(G * q_own, m, D, code, arena.local(ExchangeArena.REQ),
+                                                            q_all_ptr, _lib.ptr(q_inv_all), c.f32.data_ptr(),
+                                                            c.inv_norm.data_ptr() if cos else None,
+                                                            exact_out.data_ptr(), C.byref(dst), st))
+                self._mark(marks, "rescore")
+                if prefetch is not None:
+                    # the next batch's pushes (started after K2, long done) are published by this barrier
+                    torch.cuda.current_stream(dev).wait_event(self._prefetched[4])
+                arena.barrier()                                                   # exact scores have landed
+                exact_in_ptr = arena.local(ExchangeArena.EXACT)
+                arena.advance()
+            else:
+                recv = comm.all_to_all(lists) if G > 1 else lists                 # [G, q_own, m+1, 2]
+                self._mark(marks, "all_to_all")
+                _lib.check(lib.qst_select_requests(q_own, G, m, kprime_all, self.n_total, recv.data_ptr(),
+                                                   req.data_ptr(), bound.data_ptr(), scratch.data_ptr(), st))
+                self._mark(marks, "requests")
+                req_in = comm.all_to_all(req) if G > 1 else req                   # [G owners, q_own, m]
+                _lib.check(lib.qst_rescore_requests(G * q_own, m, D, code, req_in.data_ptr(), q_all_ptr,
+                                                    _lib.ptr(q_inv_all), c.f32.data_ptr(),
+                                                    c.inv_norm.data_ptr() if cos else None, exact_out.data_ptr(), st))
+                self._mark(marks, "rescore")
+                if prefetch is not None:
+                    # the next batch's pushes (started after K2, long done) are published by this exchange
+                    torch.cuda.current_stream(dev).wait_event(self._prefetched[4])
+                exact_in = comm.all_to_all(exact_out) if G > 1 else exact_out     # [G shards, q_own, m]
+                exact_in_ptr = exact_in.data_ptr()
             vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
             margin = torch.empty(q_own, dtype=torch.float32, device=dev)
             _lib.check(lib.qst_finalize_exact(q_own, G, m, k, code, D, self.n_total, req.data_ptr(),
-                                              exact_in.data_ptr(), bound.data_ptr(), own_f32_ptr,
+                                              exact_in_ptr, bound.data_ptr(), own_f32_ptr,
                                               own_err_ptr, self.global_stats.data_ptr(),
                                               vals.data_ptr(), idx.data_ptr(), margin.data_ptr(), st))
             self._mark(marks, "replies+finalize")
@@ -637,8 +739,14 @@ class ShardedCorpus:
             pq = scoring.prepare_rows(own_queries, scoring.QUERY_PREP[score])
             q_bf16 = self.comm.all_gather(pq.bf16) if G > 1 else pq.bf16
             self._mark(marks, "prep+gather_q")
-            lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks)
-            recv = self.comm.all_to_all(lists) if G > 1 else lists                # [G, q_own, m+1, 2]
+            lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks, fused=G > 1)
+            if isinstance(lists, ExchangeArena):
+                lists.barrier()                     # the lists were stored into their owners' buffers by the kernel
+                recv_ptr = lists.local(ExchangeArena.LISTS)
+                lists.advance()
+            else:
+                recv = self.comm.all_to_all(lists) if G > 1 else lists            # [G, q_own, m+1, 2]
+                recv_ptr = recv.data_ptr()
             self._mark(marks, "all_to_all")
             vals = torch.empty((q_own, k), dtype=torch.float32, device=dev)
             idx = torch.empty((q_own, k), dtype=torch.int64, device=dev)
@@ -646,7 +754,7 @@ class ShardedCorpus:
             scratch = self._ws(lib.qst_finalize_lists_scratch_bytes(q_own, G), "lists")
             mst = self.master
             q_inv = pq.inv_norm if cos else None
-            _lib.check(lib.qst_finalize_lists(q_own, G, m, k, kprime_all, code, self.index.d, recv.data_ptr(),
+            _lib.check(lib.qst_finalize_lists(q_own, G, m, k, kprime_all, code, self.index.d, recv_ptr,
                                               pq.f32.data_ptr(), _lib.ptr(q_inv), pq.err.data_ptr(),
                                               mst.f32.data_ptr(), mst.inv_norm.data_ptr() if cos else None,
                                               mst.stats.data_ptr(), vals.data_ptr(), idx.data_ptr(),

@@ -108,6 +108,7 @@ def test_struct_layouts():
     assert qst_b200._lib.TopkPlan.ws_bytes.offset % 8 == 0
     assert C.sizeof(qst_b200._lib.TopkPlan) == 32 + 4 * 14 + 8 * 5 + 8     # + qs flag and padding
     assert qst_b200._lib.TopkPlan.qs.offset == 32 + 4 * 14 + 8 * 5
+    assert C.sizeof(qst_b200._lib.Scatter) == 16 * 8 + 4 + 4 + 8 and qst_b200._lib.Scatter.rows_per_block.offset == 136
 
 
 def test_product_refuses_cpu_tensors_and_has_no_oracle_dependency():

@@ -54,6 +54,7 @@ def _worker(rank, world, port, out_dir):
             torch.testing.assert_close(v2.cpu()[: hi_real - lo], want_val[lo:hi_real], rtol=0, atol=2e-6)
             assert (i2.cpu()[: hi_real - lo] != want_idx[lo:hi_real]).float().mean() < 1e-3
             assert bool((m2 > 0).all())
+            assert corp._arena is not None, "one node: the exchanges must run fused over peer memory"
             if full is None:
                 # a stream of batches, each announced one call ahead (K1 + copy-engine distribution of
                 # batch t+1 underneath the exchanges of batch t): same rankings, and the path was taken

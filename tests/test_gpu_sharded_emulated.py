@@ -36,6 +36,8 @@ def _run(G, q, c, k, score, master, strategy="owners", owned=False, query_tile=1
         else:
             v, i, m = corp.topk(q_dev, k, strategy=strategy)
         torch.cuda.synchronize()
+        if G > 1 and strategy == "owners":
+            assert corp._arena is not None, "the exchanges must have been fused into their producer kernels"
         return v.cpu(), i.cpu(), m.cpu(), corp.last_rescanned
 
     return comm.run_local_world(G, body)
@@ -239,3 +241,63 @@ def test_sharded_host_pipeline_with_and_without_lookahead(lookahead):
         lo, hi = rank * q_own, (rank + 1) * q_own
         for b, (v, i) in enumerate(out):
             assert_same_ranking(i, v, want[b][1][lo:hi], want[b][0][lo:hi], f"pipeline batch {b} rank {rank}")
+
+
+def test_peer_barrier_and_scatter_descriptor_through_the_c_abi():
+    """``qst_peer_barrier`` itself (the emulated ranks above meet on the host instead): two "ranks" = two
+    streams of this process with one flag array each; each barrier completes only when both have signalled.
+    And ``qst_rescore_requests_scatter`` against the plain call + the all-to-all it replaces."""
+    import ctypes as C
+    import qst_b200
+    from qst_b200 import _lib
+    lib = _lib.load()
+    dev = _dev()
+    flags = [torch.zeros(_lib.QST_MAX_WORLD, dtype=torch.int32, device=dev) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    import time
+    torch.cuda.synchronize()
+
+    def launch(r, epoch):
+        sc = _lib.Scatter()
+        sc.base[0], sc.base[1] = flags[0].data_ptr(), flags[1].data_ptr()
+        sc.world, sc.rank, sc.rows_per_block = 2, r, 1
+        _lib.check(lib.qst_peer_barrier(C.byref(sc), epoch, streams[r].cuda_stream))    # no torch call in between:
+
+    for epoch in (1, 2, 3):                                    # anything that drains stream 0 would wait for ever
+        launch(0, epoch)
+        time.sleep(0.05)
+        assert not streams[0].query(), "rank 0 must still be waiting: rank 1 has not signalled this epoch"
+        launch(1, epoch)
+        streams[0].synchronize()
+        streams[1].synchronize()
+    assert flags[0][:2].tolist() == [3, 3] and flags[1][:2].tolist() == [3, 3]
+    launch(1, 3)                                               # a rank already signalled for: returns at once
+    streams[1].synchronize()
+
+    # scatter: G = 2 ranks' rescoring outputs land where an all-to-all would have put them
+    g = torch.Generator().manual_seed(2)
+    G, q_own, m, D, n = 2, 37, 24, 64, 500
+    c = torch.randn(n, D, generator=g).to(dev)
+    q_all = torch.randn(G * q_own, D, generator=g).to(dev)
+    recv = [torch.full((G * q_own, m), float("nan"), device=dev) for _ in range(G)]
+    want = [torch.empty((G * q_own, m), device=dev) for _ in range(G)]
+    for r in range(G):
+        req = torch.randint(-1, n, (G * q_own, m), generator=g, dtype=torch.int32).to(dev)
+        _lib.check(lib.qst_rescore_requests(G * q_own, m, D, _lib.QST_SCORE_DOT, req.data_ptr(), q_all.data_ptr(), None,
+                                            c.data_ptr(), None, want[r].data_ptr(), _lib.stream_ptr(dev)))
+        sc = _lib.Scatter()
+        for o in range(G):
+            sc.base[o] = recv[o].data_ptr()
+        sc.world, sc.rank, sc.rows_per_block = G, r, q_own
+        staging = torch.empty((G * q_own, m), device=dev)
+        _lib.check(lib.qst_rescore_requests_scatter(G * q_own, m, D, _lib.QST_SCORE_DOT, req.data_ptr(), q_all.data_ptr(),
+                                                    None, c.data_ptr(), None, staging.data_ptr(), C.byref(sc),
+                                                    _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    for o in range(G):       # owner o received block o of every rank r, at block position r
+        for r in range(G):
+            assert torch.equal(recv[o][r * q_own:(r + 1) * q_own], want[r][o * q_own:(o + 1) * q_own])
+    # a descriptor that does not cover the rows is refused
+    sc.rows_per_block = q_own + 1
+    assert lib.qst_rescore_requests_scatter(G * q_own, m, D, _lib.QST_SCORE_DOT, req.data_ptr(), q_all.data_ptr(), None,
+                                            c.data_ptr(), None, staging.data_ptr(), C.byref(sc), _lib.stream_ptr(dev)) != 0
