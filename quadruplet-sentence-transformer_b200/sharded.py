@@ -8,15 +8,21 @@ threads of one process for the single-GPU test tier.
 
 ``ShardedCorpus.topk_owned`` (data-parallel entry: every rank brings the queries it owns):
 
-1. all-gather of the fp32 queries, K1 on all G*q of them;
+1. query distribution: K1 on the rank's own slice; bf16 operand + inverse norms all-gathered, fp32 rows
+   pushed to every rank by the copy engines underneath K2 (``PeerGather``).  A stream of batches announces
+   the next one (``prefetch=``): then all of it is pushed underneath the CURRENT K2 and a step starts with
+   no collective at all;
 2. K2 of all queries against the local shard; thresholds are shared between the shards THROUGH PEER
    MEMORY while the kernels run (``qst_score_select_peers``);
-3. every shard lists its m best candidates per query by bf16 key (``qst_select_candidates``); ONE
-   all-to-all routes each query's G lists to the rank that owns the query;
-4. sharded master: the owner selects the k' best overall and sends every shard the rows it wants
-   rescored (``qst_select_requests`` -> all-to-all), the shard computes their exact fp32 scores from its
-   own rows (``qst_rescore_requests``) -> all-to-all -> ``qst_finalize_exact`` orders them and evaluates
-   the certificate.  Rescoring work per rank is q*k' rows whatever G is; per-GPU memory is the shard only.
+3. every shard lists its m best candidates per query by bf16 key and the kernel stores each list straight
+   into the receive buffer of the rank that owns the query (``qst_select_candidates_scatter``,
+   ``ExchangeArena``); a flag barrier over peer memory (``qst_peer_barrier``) is what is left of the
+   all-to-all.  Without peer-mapped memory: ``qst_select_candidates`` + ONE all-to-all;
+4. sharded master: the owner selects the k' best overall and stores into every shard's buffer the rows it
+   wants rescored (``qst_select_requests_scatter`` -> barrier), the shard computes their exact fp32 scores
+   from its own rows and stores them into the owners' buffers (``qst_rescore_requests_scatter`` ->
+   barrier), ``qst_finalize_exact`` orders them and evaluates the certificate.  Rescoring work per rank is
+   q*k' rows whatever G is; per-GPU memory is the shard only.
    Replicated master (``full_master=``, 3 GB per 1M x 768 rows on every rank): the owner
    rescoring-finalises the lists itself (``qst_finalize_lists``), no requests travel;
 5. queries whose certificate failed are re-scanned exactly -- by every shard over its own rows, merged
@@ -444,9 +450,9 @@ class ShardedCorpus:
         batches should use it and call ``finish_exact()`` after the last one.
 
         ``prefetch`` (sharded master, peer-mapped buffers available): this rank's slice of the NEXT batch
-        -- same shape on every rank, and every rank passes one or none.  Its K1 and the distribution of
-        its fp32 rows / bf16 operand / inverse norms to all ranks (copy engines, no SM) run on a side
-        stream while this call's exchanges and exact rescoring occupy the main stream, so the next call
+        -- same shape on every rank, and every rank passes one or none.  Its K1 runs in front of this
+        call's K2 and the distribution of its fp32 rows / bf16 operand / inverse norms to all ranks (copy
+        engines, no SM) underneath it, so the next call
         -- when it is given that very tensor, unmodified -- starts K2 at once instead of after an
         all-gather (any other tensor: the prefetched batch is discarded; like every collective, all
         ranks must make the same sequence of calls).  A query set processed in tiles passes tile t+1
@@ -505,23 +511,15 @@ class ShardedCorpus:
     def _tensor_key(t: torch.Tensor):
         return (t.data_ptr(), tuple(t.shape), t.dtype, t._version)
 
-    def _start_prefetch(self, nxt: torch.Tensor, gather: PeerGather, after: torch.cuda.Event):
-        """K1 of the next batch's slice + copy-engine pushes of all three regions, on the gather's side
-        stream, ordered after `after` (this step's K2 + candidate selection)."""
+    def _start_prefetch(self, nxt: torch.Tensor, gather: PeerGather):
+        """K1 of the next batch's slice on the current stream (50 us, in front of this step's K2), then the
+        copy-engine pushes of all three regions on the gather's side stream: they run underneath K2 (the
+        8-GPU case moves 7 x 46 MB per rank, ~1.5 ms of copy-engine time -- started after K2 it would land
+        on the critical path of the exchanges)."""
         dev = self.index.device
         score = self.score
-        main = torch.cuda.current_stream(dev)
-        side = gather.side if gather.side is not None else main
-        if side is not main:
-            side.wait_event(after)
-        with torch.cuda.stream(side):
-            pq = scoring.prepare_rows(nxt.to(dev).float().contiguous(), scoring.QUERY_PREP[score])
-            k1_done = torch.cuda.Event()
-            k1_done.record(side)
-        for t in (pq.f32, pq.bf16, pq.inv_norm, pq.err):
-            if t is not None:
-                t.record_stream(main)
-        ptrs, pushed = gather.push([pq.f32, pq.bf16, pq.inv_norm if score == "cos_sim" else None], after=k1_done)
+        pq = scoring.prepare_rows(nxt.to(dev).float().contiguous(), scoring.QUERY_PREP[score])
+        ptrs, pushed = gather.push([pq.f32, pq.bf16, pq.inv_norm if score == "cos_sim" else None])
         self._prefetched = (self._tensor_key(nxt), nxt.shape[0], pq, ptrs, pushed)
 
     def _topk_owned_sharded(self, own_queries, k, kprime, exact, prefetch=None):
@@ -576,13 +574,13 @@ class ShardedCorpus:
                 q_all_ptr, pushed, q_bf16, q_inv_all = pq.f32.data_ptr(), None, pq.bf16, (pq.inv_norm if cos else None)
                 own_f32_ptr, own_err_ptr = pq.f32[own].data_ptr(), pq.err[own].data_ptr()
                 keep = (pq,)
+            if prefetch is not None:
+                # safe with respect to the other ranks' reads of the buffers being overwritten: this call's
+                # finish_exact() above was the last (collective) reader of the previous generation
+                self._start_prefetch(prefetch, gather)
             self._mark(marks, "gather_q+prep")
             lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks, fused=G > 1)
             arena = lists if isinstance(lists, ExchangeArena) else None
-            if prefetch is not None:
-                sel_done = torch.cuda.Event()
-                sel_done.record()
-                self._start_prefetch(prefetch, gather, sel_done)
             if pushed is not None:
                 # this rank's pushes are done before it enters the exchange; the exchange completes only
                 # after every rank has entered it, i.e. after every rank's pushes are done
@@ -611,7 +609,7 @@ class ShardedCorpus:
                                                             exact_out.data_ptr(), C.byref(dst), st))
                 self._mark(marks, "rescore")
                 if prefetch is not None:
-                    # the next batch's pushes (started after K2, long done) are published by this barrier
+                    # the next batch's pushes (underneath K2, long done) are published by this barrier
                     torch.cuda.current_stream(dev).wait_event(self._prefetched[4])
                 arena.barrier()                                                   # exact scores have landed
                 exact_in_ptr = arena.local(ExchangeArena.EXACT)
@@ -628,7 +626,7 @@ class ShardedCorpus:
                                                     c.inv_norm.data_ptr() if cos else None, exact_out.data_ptr(), st))
                 self._mark(marks, "rescore")
                 if prefetch is not None:
-                    # the next batch's pushes (started after K2, long done) are published by this exchange
+                    # the next batch's pushes (underneath K2, long done) are published by this exchange
                     torch.cuda.current_stream(dev).wait_event(self._prefetched[4])
                 exact_in = comm.all_to_all(exact_out) if G > 1 else exact_out     # [G shards, q_own, m]
                 exact_in_ptr = exact_in.data_ptr()
