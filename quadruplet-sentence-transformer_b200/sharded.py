@@ -150,9 +150,13 @@ class PeerGather:
     rank takes part only after ITS pushes have completed -- so every block has landed.  A step that knows
     the NEXT batch (``topk_owned(..., prefetch=)``) pushes all three regions of that batch while its own
     exchanges run, and the next step starts K2 straight from the gathered buffers: no collective in front
-    of K2 at all.  Two generations alternate between pushes: a rank can be at most one step ahead of
-    another (there are collectives in every step), so a fast rank never writes into a buffer a slow rank
-    is still reading."""
+    of K2 at all.  Three generations rotate between pushes: a rank can be at most one step ahead of
+    another (there are collectives / barriers in every step), so a fast rank never writes into a buffer a
+    slow rank is still reading -- and the generation of step i is still intact while step i+1 runs (its
+    prefetch writes the third one), which is what lets the deferred exact re-scan of step i wait until
+    K2 of step i+1 has been queued."""
+
+    GENERATIONS = 3
 
     def __init__(self, region_bytes: Sequence[int], comm: Comm, device: torch.device, own_stream: bool):
         self.region_bytes, self.comm, self.device = tuple(int(b) for b in region_bytes), comm, device
@@ -161,7 +165,7 @@ class PeerGather:
             self.region_off.append(off)
             off += ((b * comm.world + 255) // 256) * 256
         self.gen_bytes = off
-        self.buffers = comm.shared_buffers(2 * self.gen_bytes, device)
+        self.buffers = comm.shared_buffers(self.GENERATIONS * self.gen_bytes, device)
         self.ok = self.buffers is not None
         self.side = torch.cuda.Stream(device=device) if (self.ok and own_stream) else None
         self.step = 0
@@ -172,7 +176,7 @@ class PeerGather:
         current stream).  Returns (this rank's gathered-buffer pointer per region for this generation,
         event to wait for before the collective that publishes the pushes)."""
         lib = _lib.load()
-        off = (self.step % 2) * self.gen_bytes
+        off = (self.step % self.GENERATIONS) * self.gen_bytes
         self.step += 1
         main = torch.cuda.current_stream(self.device)
         st = self.side if self.side is not None else main
@@ -526,10 +530,14 @@ class ShardedCorpus:
         lib = _lib.load()
         dev = self.index.device
         comm, G, r = self.comm, self.world, self.rank
-        self.finish_exact()                 # the previous call's deferred certificate check, if any
         pre, self._prefetched = getattr(self, "_prefetched", None), None
         if pre is not None and pre[0] != self._tensor_key(own_queries):
             pre = None      # not the batch that was announced (or modified since): discarded, plain path
+        if pre is None:
+            self.finish_exact()             # the previous call's deferred certificate check, if any
+        # (a prefetched batch: that check waits until this call's K2 has been queued -- the host read of the
+        #  previous step's flag then costs the GPU nothing; the previous step's gathered queries stay intact,
+        #  this call's prefetch writes the third generation)
         own_queries = own_queries.to(dev)
         q_own = own_queries.shape[0]
         q_pad = q_own * G
@@ -581,6 +589,8 @@ class ShardedCorpus:
             self._mark(marks, "gather_q+prep")
             lists, m, kprime_all = self._select_pass(q_bf16, q_pad, k, kprime, marks, fused=G > 1)
             arena = lists if isinstance(lists, ExchangeArena) else None
+            if pre is not None:
+                self.finish_exact()         # previous call's deferred check, underneath this call's K2
             if pushed is not None:
                 # this rank's pushes are done before it enters the exchange; the exchange completes only
                 # after every rank has entered it, i.e. after every rank's pushes are done

@@ -301,3 +301,41 @@ def test_peer_barrier_and_scatter_descriptor_through_the_c_abi():
     sc.rows_per_block = q_own + 1
     assert lib.qst_rescore_requests_scatter(G * q_own, m, D, _lib.QST_SCORE_DOT, req.data_ptr(), q_all.data_ptr(), None,
                                             c.data_ptr(), None, staging.data_ptr(), C.byref(sc), _lib.stream_ptr(dev)) != 0
+
+
+def test_deferred_rescan_of_a_prefetched_stream_happens_under_the_next_k2():
+    """Near-tie data (certificates fail), ``exact="deferred"`` and ``prefetch=`` together: the re-scan of
+    batch t runs inside call t+1 AFTER that call's K2 was queued and after its prefetch has pushed batch
+    t+2 -- the gathered queries of batch t must still be intact (third generation of the gather buffers)."""
+    import qst_b200
+    from qst_b200 import comm, sharded
+    g = torch.Generator().manual_seed(3)
+    N, D, k, G, q_own = 6000, 64, 10, 2, 20
+    cent = torch.randn(30, D, generator=g)
+    c = cent[torch.randint(0, 30, (N,), generator=g)] + 1e-4 * torch.randn(N, D, generator=g)
+    batches = [cent[torch.randint(0, 30, (G * q_own,), generator=g)] + 1e-3 * torch.randn(G * q_own, D, generator=g)
+               for _ in range(4)]
+    want = [_oracle_topk(b, c, k, "cos_sim") for b in batches]
+    dev = _dev()
+    c_dev = c.to(dev)
+    b_dev = [b.to(dev) for b in batches]
+
+    def body(cm):
+        s, e = sharded.shard_bounds(N, cm.world, cm.rank)
+        corp = sharded.ShardedCorpus(c_dev[s:e], N, "cos_sim", comm=cm)
+        own = [b[cm.rank * q_own:(cm.rank + 1) * q_own] for b in b_dev]
+        out, rescanned = [], 0
+        for t in range(4):
+            out.append(corp.topk_owned(own[t], k, exact="deferred", prefetch=own[t + 1] if t < 3 else None))
+            rescanned += corp.last_rescanned
+        rescanned += corp.finish_exact()
+        torch.cuda.synchronize()
+        return [(v.cpu(), i.cpu(), m.cpu()) for v, i, m in out], rescanned
+
+    res = comm.run_local_world(G, body)
+    for rank, (out, rescanned) in enumerate(res):
+        assert rescanned > 0, "the data is meant to leave queries uncertified after the first pass"
+        for b, (v, i, m) in enumerate(out):
+            lo, hi = rank * q_own, (rank + 1) * q_own
+            assert_same_ranking(i, v, want[b][1][lo:hi], want[b][0][lo:hi], f"batch {b} rank {rank}")
+            assert bool((m > 0).all())
