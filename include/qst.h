@@ -78,8 +78,12 @@ typedef struct qst_quad_params {
 
 #define QST_QUAD_SAVED_PER_ROW 8 /* 6 distances + 2 pad floats saved by fwd for bwd */
 
-/* Scratch for the cross-row reduction: must be zero-filled ONCE when allocated; the kernels
- * leave it zeroed again.  Size does not depend on B. */
+/* Scratch for the cross-row reduction ('mean' / 'sum'): must be zero-filled ONCE when allocated; the
+ * kernels leave it ready for the next launch.  One workspace serves one stream at a time.  Size does
+ * not depend on B.  The result is bitwise reproducible: per-CTA partial sums are combined either in a
+ * fixed order or (fwd_bwd on rows of <= 1024 fp32 / 2048 half elements) as 128-bit fixed-point integers
+ * carried in atomics, whose sum does not depend on arrival order.  A NaN or inf in the inputs makes the
+ * loss NaN / inf as torch's clamp_min does. */
 size_t qst_quadruplet_workspace_bytes(void);
 
 /* Forward.  loss_out: [B] (QST_RED_NONE) or [1].  saved: [B, QST_QUAD_SAVED_PER_ROW] fp32 or

@@ -2,6 +2,9 @@
 //
 // Replaces /root/reference/models/losses/losses.py:9-69 (three F.triplet_margin_loss calls and the
 // reductions) and the autograd graph behind them; kernels in quad_loss_kernels.cuh.
+#include <cstdlib>
+#include <cstring>
+
 #include "quad_loss_kernels.cuh"
 
 namespace qst {
@@ -49,6 +52,10 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
       if (dev >= 0 && dev < 64) sms_of[dev] = sms;
     }
     if (grid > sms * 3) grid = sms * 3;
+    if (grid > kQuadLimbMaxBlocks) grid = kQuadLimbMaxBlocks;
+    // A/B switch for profiles/loss_probe.py: the fence + ticket reduction of rounds 1-2
+    static const int ticket = [] { const char* e = getenv("QST_LOSS_REDUCE"); return (e && !strcmp(e, "ticket")) ? 1 : 0; }();
+    a.ticket_reduce = ticket;
   }
   if (dtype == QST_F32) quad_launch_f32(kind, a, pm, vec_ok, reg_path, grid, st);
   else if (dtype == QST_F16) quad_launch_f16(kind, a, pm, vec_ok, reg_path, grid, st);

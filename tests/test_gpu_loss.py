@@ -165,3 +165,45 @@ def test_validation_matches_reference():
         m.reduction = "x"
     with pytest.raises(qst_b200.QstError):
         m(*[x.cpu() for x in xs])   # no CPU fallback
+
+
+def test_cross_cta_reduction_sequences_reproducibility_and_out_of_range_partials():
+    """The fused kernel's 'mean' / 'sum' travel through integer limbs in four atomics (no fence, no ticket):
+    launches of different grid sizes on ONE workspace, the same input twice (bitwise equal), and the
+    partial sums the limbs cannot express -- beyond 2^63, inf, NaN -- which must come out as the
+    reference's float arithmetic gives them (slot path), followed by an ordinary launch again."""
+    import qst_b200
+    from oracle import loss_oracle
+    dev = _dev()
+    kw = dict(gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5, swap=True)
+
+    def batch(B, D, seed):
+        g = torch.Generator().manual_seed(seed)
+        return [torch.randn(B, D, generator=g) for _ in range(4)]
+
+    def run(xs, **over):
+        k = dict(kw, **over)
+        want = loss_oracle.gamma_quadruplet_loss(*xs, **k)
+        got, _ = qst_b200.gamma_quadruplet_loss_and_grads(*[x.to(dev) for x in xs], **k)
+        return got, want
+
+    for B, red in [(4096, "mean"), (5, "sum"), (1000, "mean"), (1, "mean"), (1777, "sum"), (4096, "sum")]:
+        xs = batch(B, 256, B)
+        got, want = run(xs, reduction=red, p=2.0)
+        _close(got, want, f"B={B} {red}")
+        again, _ = run(xs, reduction=red, p=2.0)
+        assert torch.equal(got, again), "same input, same workspace: bitwise equal"
+
+    xs = batch(600, 256, 7)
+    big = [x * 1e17 for x in xs]                      # p=1 distances ~1e19..1e20 per row: beyond the limbs, finite in fp32
+    got, want = run(big, reduction="mean", p=1.0)
+    rows = loss_oracle.gamma_quadruplet_loss(*big, **dict(kw, reduction="none", p=1.0))
+    assert torch.isfinite(want) and int((rows.view(150, 4).sum(1) > 9.3e18).sum()) > 0   # a CTA sums four rows
+    _close(got, want, "partials beyond 2^63")
+    for bad in (float("nan"), float("inf")):
+        ys = [x.clone() for x in xs]
+        ys[1][17, 3] = bad
+        got, want = run(ys, reduction="sum", p=2.0)
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6, equal_nan=True)
+    got, want = run(xs, reduction="mean", p=2.0)     # the words were left clean
+    _close(got, want, "after the slot path")
