@@ -81,9 +81,9 @@ typedef struct qst_quad_params {
 /* Scratch for the cross-row reduction ('mean' / 'sum'): must be zero-filled ONCE when allocated; the
  * kernels leave it ready for the next launch.  One workspace serves one stream at a time.  Size does
  * not depend on B.  The result is bitwise reproducible: per-CTA partial sums are combined either in a
- * fixed order or (fwd_bwd on rows of <= 1024 fp32 / 2048 half elements) as 128-bit fixed-point integers
- * carried in atomics, whose sum does not depend on arrival order.  A NaN or inf in the inputs makes the
- * loss NaN / inf as torch's clamp_min does. */
+ * fixed order or (fwd_bwd on rows of <= 1024 fp32 / 2048 half elements) as fixed-point integers carried
+ * in atomics, whose sum does not depend on arrival order.  A NaN or inf in the inputs makes the loss
+ * NaN / inf as torch's clamp_min and float addition do. */
 size_t qst_quadruplet_workspace_bytes(void);
 
 /* Forward.  loss_out: [B] (QST_RED_NONE) or [1].  saved: [B, QST_QUAD_SAVED_PER_ROW] fp32 or

@@ -23,11 +23,11 @@ ws = torch.zeros(lib.qst_quadruplet_workspace_bytes(), dtype=torch.uint8, device
 prm = quad_loss._params(0.6, 1.0, 0.5, 0.5, 2.0, False)
 
 
-def fused(st, red):
+def fused(st, red, upstream=1.0):
     for i in range(sets):
         x, gr = data[i], grads[i]
         _lib.check(lib.qst_quadruplet_fwd_bwd(x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), x[3].data_ptr(),
-                                              _lib.QST_F32, B, D, C.byref(prm), red, 1.0, loss[i * B:].data_ptr(),
+                                              _lib.QST_F32, B, D, C.byref(prm), red, upstream, loss[i * B:].data_ptr(),
                                               gr[0].data_ptr(), gr[1].data_ptr(), gr[2].data_ptr(),
                                               gr[3].data_ptr(), ws.data_ptr(), st))
 
@@ -66,6 +66,17 @@ import pynvml
 pynvml.nvmlInit()
 NV = pynvml.nvmlDeviceGetHandleByIndex(0)
 timeit("torch copy 50MB->50MB", copies)
+# QST_LOSS_REDUCE is read at every call, i.e. when the graph is captured
+modes = os.environ.get("QST_PROBE_MODES", "default").split(",")
 for rep in range(2):
-    timeit("fused loss mean (reg path)", lambda st: fused(st, _lib.QST_RED_MEAN))
+    for mode in modes:
+        if mode == "default":
+            os.environ.pop("QST_LOSS_REDUCE", None)
+        else:
+            os.environ["QST_LOSS_REDUCE"] = mode
+        timeit(f"fused loss mean [{mode}]", lambda st: fused(st, _lib.QST_RED_MEAN))
     timeit("fused loss none (no reduction)", lambda st: fused(st, _lib.QST_RED_NONE))
+    if os.environ.get("QST_PROBE_EXTRA"):   # is it the reduction or the VALUES of the gradients (x 1/B under 'mean')?
+        timeit("fused loss sum", lambda st: fused(st, _lib.QST_RED_SUM))
+        timeit("fused loss mean, upstream = B", lambda st: fused(st, _lib.QST_RED_MEAN, float(B)))
+        timeit("fused loss none, upstream = 1/B", lambda st: fused(st, _lib.QST_RED_NONE, 1.0 / B))

@@ -53,9 +53,11 @@ static int quad_dispatch(int kind, QuadArgs& a, int dtype, cudaStream_t st) {
     }
     if (grid > sms * 3) grid = sms * 3;
     if (grid > kQuadLimbMaxBlocks) grid = kQuadLimbMaxBlocks;
-    // A/B switch for profiles/loss_probe.py: the fence + ticket reduction of rounds 1-2
-    static const int ticket = [] { const char* e = getenv("QST_LOSS_REDUCE"); return (e && !strcmp(e, "ticket")) ? 1 : 0; }();
-    a.ticket_reduce = ticket;
+    // A/B switch for profiles/loss_probe.py, read per call (tens of nanoseconds) so that the probe can switch
+    // inside one process
+    const char* e = getenv("QST_LOSS_REDUCE");
+    const int mode = (e && !strcmp(e, "ticket")) ? 1 : 0;
+    a.reduce_mode = mode;
   }
   if (dtype == QST_F32) quad_launch_f32(kind, a, pm, vec_ok, reg_path, grid, st);
   else if (dtype == QST_F16) quad_launch_f16(kind, a, pm, vec_ok, reg_path, grid, st);

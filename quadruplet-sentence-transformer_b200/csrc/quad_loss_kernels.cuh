@@ -20,13 +20,15 @@ enum Kind { K_FWD = 0, K_BWD = 1, K_FUSED = 2 };
 constexpr int kQuadThreads = 128;          // 4 warps = 4 rows in flight per CTA
 constexpr int kQuadMaxBlocks = 148 * 16;   // grid cap (persistent over rows) -> fixed-size workspace
 
+constexpr int kQuadLimbs = 7;                    // 7 x 32 bits: 64 fractional + 160 integer bits, |x| < 2^160
 struct QuadWorkspace {
   unsigned int counter;                          // ticket protocol (generic kernels)
-  unsigned int epoch;                            // launches served by the limb protocol (tags the slots)
+  unsigned int pad;
   double partial[kQuadMaxBlocks];
-  // limb protocol (register-resident fused kernel), see limbs_issue / limbs_finish
-  unsigned long long limb[4];                    // [arrivals:10 | out-of-range CTAs:11 (limb 3 only) | sum:43]
-  unsigned long long slot[kQuadMaxBlocks];       // (tag << 32) | fp32 bits of the CTA's partial sum
+  // limb protocol (register-resident fused kernel), see limbs_issue / limbs_finish:
+  // words 0..6 sum the limbs of the non-negative partials, 7..13 those of the negative ones (magnitudes);
+  // every word: [arrivals:10 | special partials:11 | sum of limbs:43]
+  unsigned long long limb[16];
 };
 constexpr int kQuadLimbMaxBlocks = 1023;         // 10-bit arrival count
 
@@ -240,7 +242,7 @@ struct QuadArgs {
   float* saved;           // fwd: out (may be null); bwd: in
   const float* grad_out;  // bwd
   QuadWorkspace* ws;
-  int ticket_reduce;      // fused register kernel: 1 = the older fence + ticket reduction (QST_LOSS_REDUCE=ticket)
+  int reduce_mode;        // fused register kernel: 0 limb reduction, 1 fence + ticket (rounds 1-2; QST_LOSS_REDUCE=ticket)
 };
 
 template <typename T, int VEC, int PM, int KIND>
@@ -358,26 +360,29 @@ __device__ __forceinline__ void post_cta_loss(const QuadArgs& g, double warp_sum
   }
 }
 
-// Cross-CTA loss reduction without a fence, without a second round trip and without anybody waiting for a
-// reply while the memory system is busy: the CTA's partial sum travels inside the atomics themselves.
-// The partial (a double, >= 0) is written as a 128-bit fixed-point number with 64 fractional bits, cut
-// into four 32-bit limbs; limb i is added to word i, whose top ten bits count arrivals.  Integer addition
-// is associative, so the four sums -- and the loss computed from them -- do not depend on the order in
-// which CTAs arrive (bitwise reproducible).
-//   limbs_issue   warp 0, BEFORE its last gradient stores (the other warps have posted their sums and gone
-//                 on): lanes 0..3 add one limb each (one atom instruction), lane 0 stores the fp32 slot.  Nothing here is ordered against the gradient stores, so nobody waits for
-//                 stores to drain (a fence would), and the reply to the atom travels while the warp issues
-//                 its stores: measured, a reply takes ~2 us when the kernel's last stores are queued in
-//                 front of it, which is what every "publish, take a ticket, wait" form of this reduction
-//                 cost (rounds 1-2: 21.0-21.5 us against 18.7 us without the reduction).
+// Cross-CTA loss reduction without a fence, without a partial array to re-read and without anybody waiting
+// for a reply while the memory system is busy: the CTA's partial sum travels inside the atomics themselves.
+// The partial (a double) is written as a sign + 224-bit fixed-point magnitude with 64 fractional bits
+// (|x| < 2^160: more than any sum of fp32 row losses can reach), cut into seven 32-bit limbs; lane i of
+// warp 0 adds limb i to word i (non-negative partials) or word 7 + i (negative ones), every lane adds an
+// arrival to the top ten bits of its word -- ONE atom instruction per CTA.  Integer addition is associative,
+// so the fourteen sums, and the loss computed from them, do not depend on the order in which CTAs arrive:
+// bitwise reproducible, and exact up to the final rounding.  NaN, +inf and -inf partials (and magnitudes of
+// 2^160 and more, which fp32 cannot hold either) are counted in the spare bits of words 0, 1 and 2 and come
+// out as float addition gives them.
+//   limbs_issue   every warp when its share of the loss is complete, i.e. BEFORE its last gradient stores.
+//                 Warps 1..3 post their sums and go on (named barrier, arrive only); warp 0 issues the atom.
+//                 Nothing is ordered against the gradient stores, so nobody waits for stores to drain (a
+//                 fence would), and the reply travels while warp 0 issues its own stores.
 //   limbs_finish  warp 0, after its stores: the CTA whose reply from word 0 says "all others have arrived"
-//                 makes sure words 1..3 show the full count too (every CTA adds to the four words with one
-//                 instruction; normally the replies already do), recombines the limbs in a fixed order,
-//                 writes the loss and zeroes the words for the next launch.
-// A partial outside [0, 2^63) or not finite cannot be expressed in the limbs: the CTA marks word 3
-// instead, and the finishing CTA then adds up the per-CTA fp32 slots in index order (every CTA stores one,
-// tagged with the launch epoch; the finisher polls a slot until the tag is this launch's) -- NaN, inf and
-// sums beyond the fixed-point range come out as a float sum gives them.
+//                 makes sure the other words show the full count too (normally the replies already do),
+//                 evaluates the limbs in a fixed order, writes the loss and zeroes the words for the next
+//                 launch.
+// What this replaced, and what the measurements said (profiles/r02_loss_limbs_vs_ticket.txt): partial store +
+// fence + ticket + last CTA re-reads the partials cost 2.4 us on top of the 18.7 us of reduction='none';
+// issuing these atomics AFTER the last stores and waiting for the reply there cost the same (a reply queued
+// behind the kernel's last stores takes ~2 us); and a first version that tagged per-CTA fallback slots
+// with a launch epoch lost 1.4 us to the single strong load that fetched the epoch at kernel start.
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -388,82 +393,79 @@ __device__ __forceinline__ unsigned long long atom_add_relaxed_u64(unsigned long
   asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
   return old;
 }
-constexpr unsigned long long kLimbOne = 1ull << 54, kLimbBad = 1ull << 43, kLimbSum = (1ull << 43) - 1;
+constexpr unsigned long long kLimbOne = 1ull << 54, kLimbSpecial = 1ull << 43, kLimbSum = (1ull << 43) - 1;
 
-// every warp of the CTA calls this once, when its share of the loss is complete.  Warp 0: lanes 0..3 each
-// add one limb to "their" word (one atom instruction for the four words; per-lane addresses also keep ptxas
-// from wrapping the atomic in its warp-aggregation code, whose closing shuffle would wait for the reply on
-// the spot).  `reply` (the word before this CTA's add) is still in flight when the function returns -- do
-// not look at it before the gradient stores have been issued; `added` is what the lane added.
-__device__ __forceinline__ void limbs_issue(const QuadArgs& g, double warp_sum_d, double* s_part, const unsigned int* s_epoch,
-                                            int warp, int lane, unsigned long long& reply, unsigned long long& added) {
+// limb `idx` (bits [32 idx, 32 idx + 32) of |x| * 2^64) of a finite double below 2^160
+__device__ __forceinline__ unsigned long long limb_of(unsigned long long mant, int expo, int idx) {
+  const int sh = expo + 12 - 32 * idx;   // position of the mantissa's lowest bit relative to the limb's
+  if (sh >= 32 || sh <= -53) return 0ull;
+  return (sh >= 0 ? (mant << sh) : (mant >> -sh)) & 0xffffffffull;
+}
+
+// `reply` (the word before this CTA's add) is still in flight when the function returns -- do not look at it
+// before the gradient stores have been issued; `added` is what the lane added.  Per-lane addresses also keep
+// ptxas from wrapping the atomic in its warp-aggregation code (it does that for a provably warp-uniform
+// address), whose closing shuffle of the reply would make the warp wait on the spot.
+__device__ __forceinline__ void limbs_issue(const QuadArgs& g, double warp_sum_d, volatile double* s_part, int warp, int lane,
+                                            unsigned long long& reply, unsigned long long& added) {
   constexpr int kWarps = kQuadThreads / 32;
   if (lane == 0) s_part[warp] = warp_sum_d;
+  // barrier.arrive / barrier.sync order the shared-memory writes before the reads (PTX: when the barrier
+  // completes, prior accesses of the arriving threads are performed relative to the participants)
   if (warp != 0) {
-    __threadfence_block();
     asm volatile("bar.arrive 1, %0;" ::"n"(kQuadThreads) : "memory");
     return;
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kQuadThreads) : "memory");
-  QuadWorkspace* ws = g.ws;
   double tot = 0.0;
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) tot += s_part[w];
-  const bool ok = tot >= 0.0 && tot < 9223372036854775808.0;   // false for NaN
-  unsigned long long hi = 0, lo = 0;
-  if (ok) {
-    hi = __double2ull_rz(tot);
-    lo = __double2ull_rz((tot - (double)hi) * 18446744073709551616.0);
-  }
-  if (lane < 4) {
-    const unsigned long long half = lane < 2 ? lo : hi;
-    added = kLimbOne | ((lane & 1) ? (half >> 32) : (half & 0xffffffffull)) | ((lane == 3 && !ok) ? kLimbBad : 0ull);
-    reply = atom_add_relaxed_u64(&ws->limb[lane], added);
-  }
-  if (lane == 0) {
-    // the epoch was read at kernel start and had arrived in shared memory before any atomic of this CTA was
-    // issued: the finisher cannot have bumped it yet (it needs this CTA's arrival first)
-    const unsigned int tag = (*s_epoch & 0x7fffffffu) | 0x80000000u;
-    *reinterpret_cast<volatile unsigned long long*>(&ws->slot[blockIdx.x]) =
-        ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint((float)tot);
+  if (lane < 2 * kQuadLimbs) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(tot);
+    const bool neg = (bits >> 63) != 0;
+    const int biased = (int)((bits >> 52) & 0x7ffull);
+    const unsigned long long frac = bits & ((1ull << 52) - 1);
+    const int expo = biased - 1023;
+    const bool is_nan = biased == 0x7ff && frac != 0;
+    const bool is_big = !is_nan && expo >= 160;            // +-inf, or beyond the limbs (and beyond fp32)
+    const int idx = lane < kQuadLimbs ? lane : lane - kQuadLimbs;
+    unsigned long long limb = 0ull;
+    if (biased != 0 && !is_nan && !is_big && neg == (lane >= kQuadLimbs)) limb = limb_of(frac | (1ull << 52), expo, idx);
+    const bool special = (lane == 0 && is_nan) || (lane == 1 && is_big && !neg) || (lane == 2 && is_big && neg);
+    added = kLimbOne | limb | (special ? kLimbSpecial : 0ull);
+    reply = atom_add_relaxed_u64(&g.ws->limb[lane], added);
   }
 }
 
 // warp 0 only, all lanes, after the warp's last gradient stores
-__device__ __forceinline__ void limbs_finish(const QuadArgs& g, unsigned long long reply, unsigned long long added,
-                                             const unsigned int* s_epoch, int lane) {
+__device__ __forceinline__ void limbs_finish(const QuadArgs& g, unsigned long long reply, unsigned long long added, int lane) {
   const unsigned int n = gridDim.x;
   const unsigned int last = __shfl_sync(0xffffffffu, (unsigned int)(reply >> 54) == n - 1 ? 1u : 0u, 0);
   if (!last) return;
   QuadWorkspace* ws = g.ws;
   unsigned long long v = reply + added;     // the word right after this CTA's add
-  if (lane < 4) {
-    while ((unsigned int)(v >> 54) != n) v = ld_volatile_u64(&ws->limb[lane]);   // words 1..3: a few adds may still be under way
+  if (lane < 2 * kQuadLimbs) {
+    while ((unsigned int)(v >> 54) != n) v = ld_volatile_u64(&ws->limb[lane]);   // a few adds may still be under way
   }
-  const unsigned long long v1 = __shfl_sync(0xffffffffu, v, 1), v2 = __shfl_sync(0xffffffffu, v, 2);
-  const unsigned long long v3 = __shfl_sync(0xffffffffu, v, 3);
-  double result;
-  if ((v3 >> 43) & 0x7ffull) {
-    const unsigned int tag = (*s_epoch & 0x7fffffffu) | 0x80000000u;
-    double acc = 0.0;
-    for (unsigned int i = lane; i < n; i += 32) {
-      unsigned long long s;
-      do { s = ld_volatile_u64(&ws->slot[i]); } while ((unsigned int)(s >> 32) != tag);
-      acc += (double)__uint_as_float((unsigned int)s);
-    }
+  // fixed evaluation order: Horner from the top limb, positive and negative side, then the difference
+  double pos = 0.0, neg = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    result = acc;
-  } else {
-    result = (((double)(v3 & kLimbSum) * 4294967296.0 + (double)(v2 & kLimbSum)) +
-              (double)(v1 & kLimbSum) * (1.0 / 4294967296.0)) + (double)(v & kLimbSum) * (1.0 / 18446744073709551616.0);
+  for (int i = kQuadLimbs - 1; i >= 0; --i) {
+    pos = pos * 4294967296.0 + (double)(__shfl_sync(0xffffffffu, v, i) & kLimbSum);
+    neg = neg * 4294967296.0 + (double)(__shfl_sync(0xffffffffu, v, kQuadLimbs + i) & kLimbSum);
   }
+  const bool any_nan = ((__shfl_sync(0xffffffffu, v, 0) >> 43) & 0x7ffull) != 0;
+  const bool any_pinf = ((__shfl_sync(0xffffffffu, v, 1) >> 43) & 0x7ffull) != 0;
+  const bool any_ninf = ((__shfl_sync(0xffffffffu, v, 2) >> 43) & 0x7ffull) != 0;
   if (lane == 0) {
+    double result = (pos - neg) * (1.0 / 18446744073709551616.0);
+    if (any_nan || (any_pinf && any_ninf)) result = __longlong_as_double(0x7ff8000000000000ll);
+    else if (any_pinf) result = __longlong_as_double(0x7ff0000000000000ll);
+    else if (any_ninf) result = __longlong_as_double((long long)0xfff0000000000000ull);
     if (g.reduction == QST_RED_MEAN) result /= (double)g.B;
     g.loss_out[0] = (float)result;
   }
-  if (lane < 4) ws->limb[lane] = 0ull;   // every CTA's adds have been counted: nobody touches the words again
-  if (lane == 4) ws->epoch = ((*s_epoch & 0x7fffffffu) + 1u) & 0x7fffffffu;
+  if (lane < 2 * kQuadLimbs) ws->limb[lane] = 0ull;   // every CTA's adds have been counted: nobody touches the words again
 }
 
 // ------------------------------------------------------------------------------------------
@@ -489,16 +491,10 @@ __global__ void __launch_bounds__(kQuadThreads, NCH <= 6 ? 3 : 2) quad_fused_reg
   const bool swap = g.prm.swap != 0;
   double block_sum = 0.0;
   __shared__ double s_part[kWarps];
-  __shared__ unsigned int s_epoch;
   bool posted = false;
-  unsigned long long reply = 0ull, added = 0ull;   // limb protocol, lanes 0..3 of warp 0: see limbs_issue
+  unsigned long long reply = 0ull, added = 0ull;   // limb protocol, lanes 0..13 of warp 0: see limbs_issue
   const int64_t row_stride = (int64_t)gridDim.x * kWarps;
-  const bool limbs = g.reduction != QST_RED_NONE && !g.ticket_reduce;
-  // launch epoch of the limb protocol: requested now, parked in shared memory once the first row's loads
-  // have come back (the value is long there by then; nobody stalls on it)
-  unsigned int epoch = 0;
-  bool epoch_parked = !(limbs && threadIdx.x == 0);
-  if (!epoch_parked) epoch = *reinterpret_cast<volatile unsigned int*>(&g.ws->epoch);
+  const bool limbs = g.reduction != QST_RED_NONE && !(g.reduce_mode & 1);
 
   for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < g.B; row += (int64_t)gridDim.x * kWarps) {
     const T* a = reinterpret_cast<const T*>(g.a) + row * D;
@@ -541,18 +537,10 @@ __global__ void __launch_bounds__(kQuadThreads, NCH <= 6 ? 3 : 2) quad_fused_reg
     const RowTerms t = row_terms(d, g.prm);
     if (lane == 0 && g.reduction == QST_RED_NONE) g.loss_out[row] = t.loss;
     block_sum += (double)t.loss;
-    if (!epoch_parked) {
-      s_epoch = epoch;
-      epoch_parked = true;
-    }
     if (g.reduction != QST_RED_NONE && row + row_stride >= g.B) {   // this warp's last row
-      if (g.ticket_reduce) {
-        post_cta_loss(g, block_sum, s_part, warp, lane);
-        posted = true;
-      } else {   // warp 0 looks at the reply after its stores (below the loop)
-        limbs_issue(g, block_sum, s_part, &s_epoch, warp, lane, reply, added);
-        posted = true;
-      }
+      if (limbs) limbs_issue(g, block_sum, s_part, warp, lane, reply, added);   // warp 0 reads the reply below the loop
+      else post_cta_loss(g, block_sum, s_part, warp, lane);
+      posted = true;
     }
 
     const float up = g.upstream * inv_b;
@@ -618,12 +606,11 @@ __global__ void __launch_bounds__(kQuadThreads, NCH <= 6 ? 3 : 2) quad_fused_reg
     }
   }
 
-  if (!epoch_parked) s_epoch = epoch;   // thread 0 had no row
   if (g.reduction != QST_RED_NONE && !posted) {   // warp had no row
-    if (g.ticket_reduce) post_cta_loss(g, block_sum, s_part, warp, lane);
-    else limbs_issue(g, block_sum, s_part, &s_epoch, warp, lane, reply, added);
+    if (limbs) limbs_issue(g, block_sum, s_part, warp, lane, reply, added);
+    else post_cta_loss(g, block_sum, s_part, warp, lane);
   }
-  if (limbs && warp == 0) limbs_finish(g, reply, added, &s_epoch, lane);
+  if (limbs && warp == 0) limbs_finish(g, reply, added, lane);
 }
 
 template <typename T, int NCH>

@@ -167,12 +167,15 @@ def test_validation_matches_reference():
         m(*[x.cpu() for x in xs])   # no CPU fallback
 
 
-def test_cross_cta_reduction_sequences_reproducibility_and_out_of_range_partials():
-    """The fused kernel's 'mean' / 'sum' travel through integer limbs in four atomics (no fence, no ticket):
-    launches of different grid sizes on ONE workspace, the same input twice (bitwise equal), and the
-    partial sums the limbs cannot express -- beyond 2^63, inf, NaN -- which must come out as the
-    reference's float arithmetic gives them (slot path), followed by an ordinary launch again."""
+def test_cross_cta_reduction_sequences_reproducibility_and_special_partials():
+    """The fused kernel's 'mean' / 'sum' travel between CTAs as fixed-point limbs inside one atomic
+    instruction per CTA (no fence, no ticket): launches of different grid sizes on ONE workspace, the same
+    input twice (bitwise equal), sums far beyond 2^63, negative partial sums (gamma outside [0, 1], reachable
+    through the C ABI only), NaN and inf rows -- which must come out as the reference's float arithmetic
+    gives them -- followed by an ordinary launch again."""
+    import ctypes as C
     import qst_b200
+    from qst_b200 import _lib, quad_loss
     from oracle import loss_oracle
     dev = _dev()
     kw = dict(gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5, swap=True)
@@ -195,15 +198,32 @@ def test_cross_cta_reduction_sequences_reproducibility_and_out_of_range_partials
         assert torch.equal(got, again), "same input, same workspace: bitwise equal"
 
     xs = batch(600, 256, 7)
-    big = [x * 1e17 for x in xs]                      # p=1 distances ~1e19..1e20 per row: beyond the limbs, finite in fp32
-    got, want = run(big, reduction="mean", p=1.0)
-    rows = loss_oracle.gamma_quadruplet_loss(*big, **dict(kw, reduction="none", p=1.0))
-    assert torch.isfinite(want) and int((rows.view(150, 4).sum(1) > 9.3e18).sum()) > 0   # a CTA sums four rows
-    _close(got, want, "partials beyond 2^63")
+    for scale in (1e17, 1e30):                         # p=1 distances ~1e20 / ~1e33 per row: far beyond 2^63, finite in fp32
+        big = [x * scale for x in xs]
+        got, want = run(big, reduction="mean", p=1.0)
+        assert torch.isfinite(want) and float(want) > 1e18
+        _close(got, want, f"partials of magnitude {scale:g}")
     for bad in (float("nan"), float("inf")):
         ys = [x.clone() for x in xs]
         ys[1][17, 3] = bad
         got, want = run(ys, reduction="sum", p=2.0)
         torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6, equal_nan=True)
     got, want = run(xs, reduction="mean", p=2.0)     # the words were left clean
-    _close(got, want, "after the slot path")
+    _close(got, want, "after the special partials")
+
+    # negative partial sums: gamma = 3 weighs the third hinge term with -2 (rejected by the Python API, not by the C ABI)
+    lib = _lib.load()
+    xd = [x.to(dev) for x in xs]
+    prm = quad_loss._params(3.0, 1.0, 0.5, 0.5, 2.0, True)
+    ws = torch.zeros(lib.qst_quadruplet_workspace_bytes(), dtype=torch.uint8, device=dev)
+    grads = [torch.empty_like(x) for x in xd]
+    out = {}
+    for name, red, n in (("none", _lib.QST_RED_NONE, 600), ("sum", _lib.QST_RED_SUM, 1), ("mean", _lib.QST_RED_MEAN, 1)):
+        out[name] = torch.empty(n, device=dev)
+        _lib.check(lib.qst_quadruplet_fwd_bwd(xd[0].data_ptr(), xd[1].data_ptr(), xd[2].data_ptr(), xd[3].data_ptr(),
+                                              _lib.QST_F32, 600, 256, C.byref(prm), red, 1.0, out[name].data_ptr(),
+                                              grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(),
+                                              grads[3].data_ptr(), ws.data_ptr(), _lib.stream_ptr(dev)))
+    rows = out["none"].double().cpu()
+    assert int((rows < 0).sum()) > 50 and int((rows > 0).sum()) > 50
+    assert float(out["sum"]) == float(rows.sum().float()) and float(out["mean"]) == float((rows.sum() / 600).float())
