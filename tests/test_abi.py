@@ -33,6 +33,53 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert sorted(qst_b200._lib.SIGNATURES) == names
 
 
+def _declared_prototypes():
+    """(return type, name, [parameter types]) of every prototype in include/qst.h, names stripped."""
+    text = open(os.path.join(ROOT, "include", "qst.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = []
+    for ret, name, args in re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(qst_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = []
+        for a in args.split(","):
+            a = re.sub(r"\bconst\b", "", a).strip()
+            if not a or a == "void":
+                continue
+            if "*" in a:
+                params.append("ptr")
+            else:
+                words = a.split()
+                params.append(" ".join(words[:-1] if len(words) > 1 else words))
+        out.append((re.sub(r"\bconst\b", "", ret).strip(), name, params))
+    return out
+
+
+def test_ctypes_signatures_agree_with_the_header():
+    """Parameter count and width of every ctypes binding against the prototype in include/qst.h: a
+    64-bit size bound as a C int, or one argument too few, corrupts a call without any error."""
+    import qst_b200
+    scalar = {"int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t, "float": C.c_float,
+              "uint32_t": C.c_uint32, "long long": C.c_longlong}
+    protos = _declared_prototypes()
+    assert sorted(n for _, n, _ in protos) == sorted(qst_b200._lib.SIGNATURES)
+
+    def is_pointer(t):
+        return t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents")      # POINTER(...) types have .contents
+
+    for ret, name, params in protos:
+        restype, argtypes = qst_b200._lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), f"{name}: {len(params)} parameters declared, {len(argtypes)} bound"
+        if "*" in ret:
+            assert is_pointer(restype), name
+        else:
+            assert restype is scalar[ret], f"{name}: returns {ret}, bound as {restype}"
+        for i, (want, got) in enumerate(zip(params, argtypes)):
+            if want in ("ptr", "qst_stream_t"):
+                assert is_pointer(got), f"{name} argument {i}: pointer declared, {got} bound"
+            else:
+                assert got is scalar[want], f"{name} argument {i}: {want} declared, {got} bound"
+
+
 def test_version_and_error_channel(lib):
     assert lib.qst_version() == 100
     assert lib.qst_padded_dim(384) == 384 and lib.qst_padded_dim(385) == 448 and lib.qst_padded_dim(1) == 64
