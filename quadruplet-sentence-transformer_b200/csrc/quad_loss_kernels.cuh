@@ -367,7 +367,7 @@ __device__ __forceinline__ void post_cta_loss(const QuadArgs& g, double warp_sum
 // warp 0 adds limb i to word i (non-negative partials) or word 7 + i (negative ones), every lane adds an
 // arrival to the top ten bits of its word -- ONE atom instruction per CTA.  Integer addition is associative,
 // so the fourteen sums, and the loss computed from them, do not depend on the order in which CTAs arrive:
-// bitwise reproducible, and exact up to the final rounding.  NaN, +inf and -inf partials (and magnitudes of
+// bitwise reproducible; the sums are exact, their evaluation rounds to double a few times.  NaN, +inf and -inf partials (and magnitudes of
 // 2^160 and more, which fp32 cannot hold either) are counted in the spare bits of words 0, 1 and 2 and come
 // out as float addition gives them.
 //   limbs_issue   every warp when its share of the loss is complete, i.e. BEFORE its last gradient stores.
