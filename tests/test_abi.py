@@ -130,6 +130,46 @@ def test_plan_invariants(lib):
     assert plan.units / (waves * groups) > 0.95
 
 
+def test_plan_invariants_hold_on_a_random_sweep(lib):
+    """5000 seeded random (Q, N, D, k, k', score, SM count) shapes incl. the awkward ones (1, 255/256/257,
+    k = 900, D = 1 / 769 / 4096, 1-16 SMs): every accepted plan tiles the problem exactly, has no empty
+    stripe, a workspace that matches its layout, and enough per-unit entries to deliver k' candidates;
+    every rejected one is rejected through the error channel."""
+    import random
+
+    import qst_b200
+    os.environ.pop("QST_SCORE_CTAS", None)
+    rng = random.Random(1)
+    accepted = 0
+    for _ in range(5000):
+        Q = rng.choice([1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 512, 1000, rng.randint(1, 5000),
+                        rng.randint(1, 200_000)])
+        N = rng.choice([1, 2, 255, 256, 257, 1000, rng.randint(1, 100_000), rng.randint(1, 20_000_000)])
+        D = rng.choice([1, 3, 8, 63, 64, 65, 100, 384, 768, 769, 832, 1024, rng.randint(1, 4096)])
+        k = rng.choice([1, 5, 10, 100, 900, rng.randint(1, 1024)])
+        kp = rng.choice([0, 0, 0, k, k + 16, rng.randint(1, 2048)])
+        score, sms = rng.choice([0, 1, 2]), rng.choice([148, 148, 148, 132, 16, 2, 1])
+        p = qst_b200._lib.TopkPlan()
+        rc = lib.qst_topk_plan_make(Q, N, D, k, kp, score, sms, C.byref(p))
+        if rc != 0:
+            assert rc == -1 and lib.qst_last_error(), (Q, N, D, k, kp)
+            continue
+        accepted += 1
+        what = (Q, N, D, k, kp, score, sms)
+        assert p.rows_per_unit == 128 * p.ctas and p.ctas in (1, 2), what
+        assert p.D_pad % 64 == 0 and p.D_pad >= D, what
+        assert p.kprime >= k and 1 <= p.kunit <= max(p.kprime, 16) and p.cap >= p.kunit, what
+        assert p.m_tiles * p.rows_per_unit >= Q > (p.m_tiles - 1) * p.rows_per_unit, what
+        assert p.n_tiles * 256 >= N > (p.n_tiles - 1) * 256, what
+        assert p.stripes >= 1 and p.stripes * p.tiles_per_stripe >= p.n_tiles, what
+        assert (p.stripes - 1) * p.tiles_per_stripe < p.n_tiles, what
+        assert p.units == p.m_tiles * p.stripes and 1 <= p.grid <= max(1, sms // p.ctas), what
+        assert p.off_thr < p.off_cnt < p.off_uthr < p.off_cand < p.ws_bytes, what
+        assert p.ws_bytes - p.off_cand == p.units * p.rows_per_unit * p.cap * 8, what
+        assert p.kunit * p.stripes >= min(p.kprime, N) or p.kunit >= min(p.kprime, N), what
+    assert accepted > 3000
+
+
 def test_plan_picks_tile_shape_and_stripes_for_small_batches(lib):
     """Without QST_SCORE_CTAS: single-CTA tiles (M=128) when the batch fits one tile or when its last
     256-row block would be at most half full (small batches only), CTA pairs otherwise; a small batch
