@@ -96,6 +96,37 @@ def test_version_and_error_channel(lib):
     assert lib.qst_padded_dim_for(768, 2) == 832 and lib.qst_padded_dim_for(768, 1) == 768
 
 
+def test_compute_entries_reject_bad_arguments_before_any_device_work(lib):
+    """No kernel is launched here (there is no GPU in this tier): every entry validates its arguments
+    first and reports through the return code + qst_last_error instead of dereferencing a null pointer."""
+    import qst_b200
+    L = qst_b200._lib
+    prm = L.QuadParams(0.6, 0.4, 1.0, 0.5, 0.5, 2.0, 1e-6, 0)
+    bad_p = L.QuadParams(0.6, 0.4, 1.0, 0.5, 0.5, -1.0, 1e-6, 0)
+    N = None
+    cases = [
+        (lambda: lib.qst_quadruplet_fwd(N, N, N, N, 7, 4, 8, C.byref(prm), 2, N, N, N, N), b"bad dtype 7"),
+        (lambda: lib.qst_quadruplet_fwd(N, N, N, N, 0, -1, 8, C.byref(prm), 2, N, N, N, N), b"bad shape"),
+        (lambda: lib.qst_quadruplet_fwd(N, N, N, N, 0, 4, 8, N, 2, N, N, N, N), b"null params"),
+        (lambda: lib.qst_quadruplet_fwd(N, N, N, N, 0, 4, 8, C.byref(prm), 2, N, N, N, N), b"null loss_out"),
+        (lambda: lib.qst_quadruplet_fwd(N, N, N, N, 0, 4, 8, C.byref(bad_p), 2, N, N, N, N), b"p must be positive"),
+        (lambda: lib.qst_quadruplet_fwd(N, N, N, N, 0, 4, 8, C.byref(prm), 5, N, N, N, N), b"bad reduction"),
+        (lambda: lib.qst_prep_rows(N, 0, 4, 8, 0, N, N, N, N, N, N), b"prep_rows"),
+        (lambda: lib.qst_score_select(N, N, N, N, N), b"score_select"),
+        (lambda: lib.qst_finalize_topk(N, N, N, N, N, N, N, N, 0, N, N, N, N), b"finalize_topk"),
+        (lambda: lib.qst_exact_rescan(4, 10, 8, 3, 0, N, N, N, N, 0, N, N, N, N, N), b"exact_rescan"),
+        (lambda: lib.qst_merge_topk(N, N, 2, 4, 10, N, N, N), b"merge_topk"),
+        (lambda: lib.qst_ir_metrics(N, 4, 10, N, N, N, 0, N, N, N, N), b"ir_metrics"),
+        (lambda: lib.qst_dense_scores(0, 10, 8, 0, N, N, N, N, N, N), b"dense_scores"),
+        (lambda: lib.qst_quadruplet_eval(N, N, N, N, 0, 4, 8, N, N, N), b"quadruplet_eval"),
+        (lambda: lib.qst_peer_barrier(N, 1, N), b"peer_barrier"),
+        (lambda: lib.qst_exchange_candidates(N, N, N, 4, 3, N), b"null argument"),
+    ]
+    for call, message in cases:
+        assert call() == -1
+        assert message in lib.qst_last_error(), (message, lib.qst_last_error())
+
+
 def test_plan_invariants(lib):
     """Host-side planning (pure arithmetic, no device): tiling, stripes, workspace layout."""
     import qst_b200
