@@ -1,5 +1,7 @@
 """Host-side logic that needs no GPU: reductions of the metric path, relevance CSR, sharding
 arithmetic, evaluator construction/validation, synthetic data determinism."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -242,3 +244,138 @@ def test_local_comm_collectives_have_the_layouts_of_the_distributed_ones():
     one = comm.SingleComm()
     t = torch.ones(2)
     assert one.all_gather(t) is t and one.all_to_all(t) is t and one.world == 1
+
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def _calls_in(path):
+    """{callee name: [(line, keywords, n positional)]} of every call in a reference source file."""
+    import ast
+    out = {}
+    for node in ast.walk(ast.parse(open(path).read())):
+        if isinstance(node, ast.Call):
+            f = node.func
+            name = f.id if isinstance(f, ast.Name) else (
+                f"{f.value.id}.{f.attr}" if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) else
+                (f.attr if isinstance(f, ast.Attribute) else None))
+            if name:
+                out.setdefault(name, []).append((node.lineno, [k.arg for k in node.keywords], len(node.args)))
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="the reference is only mounted in the authoring container")
+def test_drop_in_signatures_accept_the_reference_call_sites():
+    """The boundary of SURVEY section 8b read from the reference's OWN source with ``ast``: every keyword the
+    reference passes at its call sites binds to the drop-in's signature (no **kwargs catch-all needed),
+    and the functional loss has the reference's parameter names, order and defaults."""
+    import inspect
+
+    import qst_b200
+
+    def binds(fn, keywords, npos=0, skip_self=True):
+        sig = inspect.signature(fn)
+        params = [p for p in sig.parameters.values()]
+        if skip_self and params and params[0].name == "self":
+            params = params[1:]
+        named = {p.name for p in params if p.kind in (p.POSITIONAL_OR_KEYWORD, p.KEYWORD_ONLY)}
+        missing = [k for k in keywords if k is not None and k not in named]
+        assert not missing, f"{fn.__qualname__} does not take {missing}"
+        assert npos <= len([p for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)])
+
+    seen = 0
+    # ir_evauation_script.py:107-123 / :130-131 and models/evaluators.py:572-604
+    for rel in ("ir_evauation_script.py", os.path.join("models", "evaluators.py")):
+        calls = _calls_in(os.path.join(REFERENCE_ROOT, rel))
+        for line, kws, npos in calls.get("InformationRetrievalEvaluator", []):
+            binds(qst_b200.InformationRetrievalEvaluator.__init__, kws, npos)
+            seen += 1
+        for line, kws, npos in calls.get("evaluator", []):                  # evaluator(model=..., output_path=...)
+            binds(qst_b200.InformationRetrievalEvaluator.__call__, kws, npos)
+            seen += 1
+        for line, kws, npos in calls.get("QuadrupletEvaluator.from_input_examples", []):
+            # a classmethod that forwards **kwargs to the constructor, here as in the reference (:225, :264)
+            binds(qst_b200.QuadrupletEvaluator.from_input_examples, [k for k in kws if k == "examples"], npos,
+                  skip_self=False)
+            binds(qst_b200.QuadrupletEvaluator.__init__, [k for k in kws if k != "examples"])
+            seen += 1
+        for line, kws, npos in calls.get("QuadrupletLossEvaluator", []):
+            binds(qst_b200.QuadrupletLossEvaluator.__init__, kws, npos)
+            seen += 1
+    assert seen >= 6
+    # models/quadruplet_sentence_transformer.py:69-75: self._quadruplet_loss(x_anchor=, x_pos=, x_part=, x_neg=, **kw)
+    calls = _calls_in(os.path.join(REFERENCE_ROOT, "models", "quadruplet_sentence_transformer.py"))
+    loss_calls = [c for c in calls.get("self._quadruplet_loss", []) if "x_anchor" in c[1]]
+    assert loss_calls
+    for line, kws, npos in loss_calls:
+        binds(qst_b200.GammaQuadrupletLoss.forward, kws, npos)
+    assert any(p.kind == p.VAR_KEYWORD for p in inspect.signature(qst_b200.GammaQuadrupletLoss.forward).parameters.values())
+
+    # the functional form and the two constructors against the reference module itself (names, order, defaults)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_losses", os.path.join(REFERENCE_ROOT, "models", "losses", "losses.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    def shape(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()
+                if p.name != "self" and p.kind is not p.VAR_KEYWORD]
+
+    assert shape(qst_b200.gamma_quadruplet_loss) == shape(ref.gamma_quadruplet_loss)
+    assert shape(qst_b200.GammaQuadrupletLoss.__init__) == shape(ref.GammaQuadrupletLoss.__init__)
+    assert shape(qst_b200.QuadrupletLoss.__init__) == shape(ref.QuadrupletLoss.__init__)
+    assert shape(qst_b200.GammaQuadrupletLoss.forward) == shape(ref.GammaQuadrupletLoss.forward)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="the reference is only mounted in the authoring container")
+def test_evaluator_signatures_match_the_reference_definitions():
+    """``models/evaluators.py`` cannot be imported here (it needs sentence-transformers and downloads a
+    cross-encoder at import time), so its definitions are read with ``ast``: parameter names, order and
+    literal defaults of ``euclidean_score``, ``QuadrupletEvaluator`` and ``QuadrupletLossEvaluator``
+    (``__init__`` and ``__call__``) equal the drop-in's."""
+    import ast
+    import inspect
+
+    import qst_b200
+
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "models", "evaluators.py")).read())
+
+    def ref_params(fn: ast.FunctionDef):
+        a = fn.args
+        names = [x.arg for x in a.posonlyargs + a.args]
+        defaults = [inspect.Parameter.empty] * (len(names) - len(a.defaults)) + list(a.defaults)
+        out = []
+        for n, d in zip(names, defaults):
+            if n in ("self", "cls"):
+                continue
+            if d is inspect.Parameter.empty:
+                out.append((n, d))
+            else:
+                try:
+                    out.append((n, ast.literal_eval(d)))
+                except ValueError:
+                    out.append((n, ast.unparse(d)))          # e.g. SimilarityFunction member / a constant name
+        for x, d in zip(a.kwonlyargs, a.kw_defaults):
+            out.append((x.arg, ast.literal_eval(d) if d is not None else inspect.Parameter.empty))
+        return out
+
+    def ours(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()
+                if p.name not in ("self", "cls") and p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL)]
+
+    def same(ref_list, our_list, what):
+        assert [n for n, _ in ref_list] == [n for n, _ in our_list][:len(ref_list)], what
+        for (n, rd), (_, od) in zip(ref_list, our_list):
+            if rd is inspect.Parameter.empty or isinstance(rd, str) and not isinstance(od, str):
+                continue                                      # required, or a non-literal default expression
+            assert rd == od, (what, n, rd, od)
+        # anything the drop-in adds must be optional
+        assert all(d is not inspect.Parameter.empty for _, d in our_list[len(ref_list):]), what
+
+    fns = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+    classes = {n.name: {m.name: m for m in n.body if isinstance(m, ast.FunctionDef)}
+               for n in tree.body if isinstance(n, ast.ClassDef)}
+    same(ref_params(fns["euclidean_score"]), ours(qst_b200.euclidean_score), "euclidean_score")
+    for cls in ("QuadrupletEvaluator", "QuadrupletLossEvaluator"):
+        for method in ("__init__", "__call__"):
+            same(ref_params(classes[cls][method]), ours(getattr(getattr(qst_b200, cls), method)), f"{cls}.{method}")
