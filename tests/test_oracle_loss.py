@@ -1,5 +1,7 @@
 """Pin the loss oracle against the reference's own outputs (committed golden vectors) and
 the identities stated by the reference's only test artefact (quadruplet_loss_test.ipynb)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -62,3 +64,45 @@ def test_validation_raises_like_reference(kw):
     xs = [torch.zeros(2, 3) for _ in range(4)]
     with pytest.raises(ValueError):
         lo.gamma_quadruplet_loss(*xs, **kw)
+
+
+@pytest.mark.skipif(not os.path.exists(lo.REFERENCE_LOSSES_PATH), reason="the reference is only mounted in the authoring container")
+def test_product_validation_messages_equal_the_reference_module_live():
+    """The drop-in (not the oracle) against the reference module itself, on the CPU: validation runs before
+    anything touches a device, so conditions, ORDER of the checks (two bad arguments at once) and message
+    texts can be compared here -- functional form, constructor and property setters
+    (models/losses/losses.py:20-32, 165-173, 181-228, 255-258)."""
+    import re
+
+    import qst_b200
+    ref = lo.load_reference_losses()
+    xs = [torch.zeros(2, 3) for _ in range(4)]
+
+    def outcome(fn):
+        try:
+            fn()
+        except ValueError as e:
+            # the text of a frozenset depends on the hash seed of the process; its members do not
+            return re.sub(r"frozenset\(\{.*?\}\)", lambda m: "frozenset" + str(sorted(re.findall(r"'(\w+)'", m.group(0)))),
+                          str(e))
+        except Exception as e:  # noqa: BLE001
+            return type(e).__name__
+        return None
+
+    cases = [dict(gamma=-0.1), dict(gamma=1.5), dict(margin_pos_neg=0), dict(margin_pos_part=-1),
+             dict(margin_part_neg=0), dict(p=0), dict(reduction="avg"), dict(gamma=2, p=-1),
+             dict(margin_pos_neg=-1, reduction="x"), dict(margin_part_neg=-3, margin_pos_part=0)]
+    for kw in cases:
+        want = outcome(lambda: ref.gamma_quadruplet_loss(*xs, **kw))
+        assert want is not None and outcome(lambda: qst_b200.gamma_quadruplet_loss(*xs, **kw)) == want, kw
+        want = outcome(lambda: ref.GammaQuadrupletLoss(**kw))
+        assert want is not None and outcome(lambda: qst_b200.GammaQuadrupletLoss(**kw)) == want, kw
+    theirs, ours = ref.GammaQuadrupletLoss(), qst_b200.GammaQuadrupletLoss()
+    for attr, val in (("margin_part_neg", 0), ("reduction", "x"), ("gamma", 3), ("p", -1), ("margin_pos_neg", 0),
+                      ("margin_pos_part", -2)):
+        want = outcome(lambda: setattr(theirs, attr, val))
+        assert want is not None and outcome(lambda: setattr(ours, attr, val)) == want, attr
+    # good values are accepted and readable on both
+    for attr, val in (("margin_part_neg", 0.25), ("reduction", "sum"), ("gamma", 1.0), ("p", 3.0), ("swap", True)):
+        setattr(theirs, attr, val), setattr(ours, attr, val)
+        assert getattr(theirs, attr) == getattr(ours, attr) == val
