@@ -1,0 +1,140 @@
+"""Run the reference's OWN in-repo evaluator code on the CPU (TEST INFRASTRUCTURE, authoring container only).
+
+``/root/reference/models/evaluators.py`` cannot be imported: it needs ``sentence-transformers==2.2.2`` (absent
+from this image) and downloads a cross-encoder at import time (``:31``).  The pieces of it that lie on the
+SURVEY section-8 path and are the reference's own code -- ``euclidean_score`` (``:392-405``),
+``QuadrupletLossEvaluator`` (``:34-128``), ``QuadrupletEvaluator`` (``:130-389``) -- are therefore lifted out
+of the file with ``ast`` AT TEST TIME (nothing is copied into this repository) and executed in a namespace in
+which only the third-party names are stand-ins:
+
+* ``TripletEvaluator`` (sentence-transformers) -> ``ScriptedTriplet``: records its constructor arguments and
+  returns the accuracy the test scripted for it (what the real one computes is restated in
+  ``oracle/quad_eval_oracle.py`` and stays unpinned);
+* ``QuadrupletSentenceTransformerLossModel`` -> ``ScriptedLossModel``: returns the per-batch loss tensors the
+  test scripted (the loss arithmetic itself is pinned by ``tests/golden/loss_golden.npz``);
+* ``SentenceEvaluator`` -> ``object``, ``InputExample`` -> a two-field class, ``tqdm`` / ``autocast`` /
+  ``batch_to_device`` -> no-ops.
+
+Everything else the lifted code executes (sampling with ``random``, the 5-epoch re-sampling, the global
+accuracy formula, the incremental mean in tensor arithmetic, CSV and JSON writing) is the reference's.
+"""
+import ast
+import contextlib
+import csv
+import enum
+import json
+import logging
+import os
+import random
+import typing
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = "/root/reference"
+EVALUATORS = os.path.join(REFERENCE_ROOT, "models", "evaluators.py")
+CONSTANTS = os.path.join(REFERENCE_ROOT, "dataset", "constants.py")
+
+
+def available() -> bool:
+    return os.path.isfile(EVALUATORS) and os.path.isfile(CONSTANTS)
+
+
+class InputExample:
+    """Stand-in for sentence_transformers.InputExample (``texts`` + ``label``)."""
+
+    def __init__(self, guid="", texts=None, label=0):
+        self.guid, self.texts, self.label = guid, texts, label
+
+
+class SimilarityFunction(enum.Enum):
+    """Members and values of sentence_transformers.evaluation.SimilarityFunction (2.2.2)."""
+    COSINE = 0
+    EUCLIDEAN = 1
+    MANHATTAN = 2
+    DOT_PRODUCT = 3
+
+
+class ScriptedTriplet:
+    """Stand-in for TripletEvaluator: ``script[name]`` is the list of accuracies its calls return, in order."""
+    script = {}
+    built = []
+
+    def __init__(self, anchors, positives, negatives, main_distance_function=None, name="", batch_size=16,
+                 show_progress_bar=False, write_csv=True):
+        self.anchors, self.positives, self.negatives, self.name = anchors, positives, negatives, name
+        self.main_distance_function, self.write_csv = main_distance_function, write_csv
+        ScriptedTriplet.built.append(self)
+
+    def __call__(self, model, output_path=None, epoch=-1, steps=-1):
+        return ScriptedTriplet.script[self.name].pop(0)
+
+
+class ScriptedLossModel:
+    """Stand-in for QuadrupletSentenceTransformerLossModel: returns the scripted batch losses in order."""
+    losses = []
+    seen_batches = []
+
+    def __init__(self, st_model, quadruplet_loss, additional_model_kwargs=None, additional_loss_kwargs=None):
+        pass
+
+    def __call__(self, features, labels):
+        ScriptedLossModel.seen_batches.append(len(labels))
+        return ScriptedLossModel.losses.pop(0)
+
+
+class StubSentenceModel:
+    """What the lifted QuadrupletLossEvaluator touches of a SentenceTransformer."""
+    device = torch.device("cpu")
+
+    @staticmethod
+    def smart_batching_collate(batch):
+        return [batch], torch.zeros(len(batch))
+
+
+class _Bar:
+    def __init__(self, it=None, **kw):
+        self._it = it
+
+    def __iter__(self):
+        return iter(self._it)
+
+    def update(self, n=1):
+        pass
+
+    def set_description(self, desc=None):
+        pass
+
+    def close(self):
+        pass
+
+
+def _constants():
+    ns = {"Final": typing.Final, "final": typing.final, "os": os}
+    tree = ast.parse(open(CONSTANTS).read())
+    body = [n for n in tree.body if isinstance(n, (ast.Assign, ast.AnnAssign, ast.Import, ast.ImportFrom))]
+    exec(compile(ast.Module(body=body, type_ignores=[]), CONSTANTS, "exec"), ns)
+    return ns
+
+
+def load(*names):
+    """Namespace in which the named top-level definitions of models/evaluators.py have been executed."""
+    consts = _constants()
+    ns = {
+        "csv": csv, "json": json, "logging": logging, "os": os, "random": random, "np": np, "torch": torch,
+        "Optional": typing.Optional, "List": typing.List, "Callable": typing.Callable, "Dict": typing.Dict,
+        "Union": typing.Union, "Set": typing.Set, "final": typing.final, "Final": typing.Final,
+        "Tensor": torch.Tensor, "DataLoader": torch.utils.data.DataLoader,
+        "SentenceTransformer": object, "SentenceEvaluator": object, "QuadrupletDataset": object,
+        "QuadrupletLoss": object, "InputExample": InputExample, "SimilarityFunction": SimilarityFunction,
+        "TripletEvaluator": ScriptedTriplet, "QuadrupletSentenceTransformerLossModel": ScriptedLossModel,
+        "tqdm": _Bar, "autocast": contextlib.nullcontext, "batch_to_device": lambda batch, device: batch,
+        "LOGGER": logging.getLogger("reference.models.evaluators"),
+    }
+    for key in ("REFERENCE_EXAMPLE", "POS_EXAMPLES", "PART_POS_EXAMPLES", "NEG_EXAMPLES", "RANDOM_SEED"):
+        ns[key] = consts[key]
+    tree = ast.parse(open(EVALUATORS).read())
+    found = {n.name: n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+    for name in names:
+        exec(compile(ast.Module(body=[found[name]], type_ignores=[]), EVALUATORS, "exec"), ns)
+    return ns

@@ -1,0 +1,155 @@
+"""The host side of SURVEY 8f row 3 (and a8) pinned to the reference's OWN code.
+
+``tests/golden/evaluators_golden.json`` holds what ``/root/reference/models/evaluators.py`` itself produces
+(``QuadrupletEvaluator`` sampling / global accuracy / CSV, ``QuadrupletLossEvaluator`` incremental mean / JSON
+log, ``euclidean_score``) when only its third-party collaborators are scripted -- see
+``tests/reference_sandbox.py`` and ``tests/golden/make_evaluators_golden.py``.  Here the drop-in classes and
+the oracle restatements are held against those vectors on the CPU (the device work underneath -- embeddings,
+the nine comparison counts, the per-batch losses -- is scripted the same way and is covered by the ``-m gpu``
+tests), and, when the reference is mounted, the fixture is re-derived from the reference and must not have
+drifted."""
+import json
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import make_evaluators_golden as gen  # noqa: E402
+import reference_sandbox as rs  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(HERE, "golden", "evaluators_golden.json")) as fp:
+        return json.load(fp)
+
+
+def test_sampling_of_quadruplets_follows_the_reference_draw_for_draw(golden):
+    """models/evaluators.py:224-262 and :264-343: same ``random`` stream -> same sentences, at construction
+    and at the re-sampling after 5 epochs (and NOT before)."""
+    import qst_b200
+    examples = gen.dict_examples(golden["sampling"]["n"])
+    random.seed(golden["sampling"]["seed"])
+    ev = qst_b200.QuadrupletEvaluator.from_input_examples(examples, gamma=0.6, name="s")
+    assert [ev.anchors, ev.positives, ev.partially_positives, ev.negatives] == golden["sampling"]["first"]
+    for epoch in range(5):
+        if epoch == 4:
+            assert [ev.anchors, ev.positives, ev.partially_positives, ev.negatives] == golden["sampling"]["first"]
+        ev._reset_examples()
+    assert [ev.anchors, ev.positives, ev.partially_positives, ev.negatives] == golden["sampling"]["after_5_epochs"]
+    # InputExample-shaped items and (item, label) pairs take the texts as they are
+    items = [(rs.InputExample(texts=[f"a{i}", f"p{i}", f"q{i}", f"n{i}"]), 0) for i in range(3)]
+    ev = qst_b200.QuadrupletEvaluator.from_input_examples(items)
+    assert ev.positives == ["p0", "p1", "p2"] and ev.negatives == ["n0", "n1", "n2"]
+
+
+# examples per call such that count / n reproduces every scripted accuracy of that call exactly
+_N_PER_CALL = [100, 81, 7, 7, 30]
+
+
+def _count(acc, n):
+    c = round(acc * n)
+    assert c / n == acc, (acc, n)
+    return c
+
+
+@pytest.mark.parametrize("main", ["COSINE", "MANHATTAN", "EUCLIDEAN", None])
+def test_quadruplet_evaluator_host_path_equals_the_reference(golden, tmp_path, monkeypatch, main):
+    """Global accuracy (:367), return value and CSV (:374-387) for scripted comparison counts: the drop-in's
+    ``__call__`` with the device work replaced by the counts that give the reference's scripted triplet
+    accuracies -- returned floats ``==``, CSV text byte for byte."""
+    import qst_b200
+    from qst_b200 import quad_evaluator as qe
+    column = {"COSINE": 0, "MANHATTAN": 1, "EUCLIDEAN": 2, None: 1}[main]
+    for case in golden["quadruplet_evaluator"]:
+        out = tmp_path / f"{main}_{case['gamma']}"
+        out.mkdir()
+        ev = qst_b200.QuadrupletEvaluator(["a"], ["p"], ["pp"], ["n"], gamma=case["gamma"], name="val",
+                                          main_distance_function=None if main is None else rs.SimilarityFunction[main])
+        monkeypatch.setattr(ev, "_encode", lambda model, sentences: None)
+        returned = []
+        for i, (epoch, steps) in enumerate(golden["calls"]):
+            n = _N_PER_CALL[i]
+            counts = torch.zeros(3, 3, dtype=torch.int64)                  # [metric, pair]; others lose (None: max)
+            for j, pair in enumerate(("pos_part", "pos_neg", "part_neg")):
+                counts[column, j] = _count(golden["triplet_script"][pair][i], n)
+            monkeypatch.setattr(qe, "paired_distance_counts", lambda *embs, _c=counts: _c)
+            ev.anchors = ev.positives = ev.partially_positives = ev.negatives = ["x"] * n
+            returned.append(ev(None, output_path=str(out), epoch=epoch, steps=steps))
+        assert returned == case["returned"]
+        assert ev.csv_file == case["csv_file"]
+        assert open(out / ev.csv_file, newline="", encoding="utf-8").read() == case["csv_text"]
+
+
+def test_loss_evaluator_running_mean_and_log_equal_the_reference(golden, tmp_path, monkeypatch):
+    """models/evaluators.py:84-128 for scripted batch losses: returned value (the reference returns the 0-dim
+    float32 tensor, the drop-in its float) and the JSON log text, two calls appending to one file."""
+    import qst_b200
+    from oracle import loss_eval_oracle
+    for case in golden["loss_evaluator"]:
+        n_batches = len(case["batch_sizes_seen"])
+        losses = golden["batch_losses"][:n_batches]
+        out = tmp_path / f"{case['n_items']}_{case['batch_size']}"
+        out.mkdir()
+        ev = qst_b200.QuadrupletLossEvaluator(list(range(case["n_items"])), None, batch_size=case["batch_size"])
+        # the drop-in batches the dataset like the reference's DataLoader does
+        from qst_b200.loss_evaluator import _batches
+        assert [len(b) for b in _batches(list(range(case["n_items"])), case["batch_size"])] == case["batch_sizes_seen"]
+        monkeypatch.setattr(ev, "batch_losses", lambda model, _l=losses: torch.tensor(_l, dtype=torch.float32))
+        first = ev(None, output_path=str(out), epoch=0, steps=-1)
+        monkeypatch.setattr(ev, "batch_losses", lambda model, _l=losses: torch.tensor(_l[::-1], dtype=torch.float32))
+        second = ev(None, output_path=str(out), epoch=1, steps=40)
+        assert [first, second] == case["returned"] and isinstance(first, float)
+        assert open(out / "_quadruplet_loss_eval.json").read() == case["json_text"]
+        # the oracle restatement of the same expression
+        for seq, want in ((losses, case["returned"][0]), (losses[::-1], case["returned"][1])):
+            got = loss_eval_oracle.running_average([torch.tensor(v, dtype=torch.float32) for v in seq])
+            assert got.dtype == torch.float32 and float(got) == want
+            assert float(qst_b200.loss_evaluator.incremental_mean_f32(np.asarray(seq, dtype=np.float32))) == want
+
+
+def test_euclidean_score_oracle_equals_the_reference_function(golden):
+    """models/evaluators.py:392-405 (tensor / list / 1-D inputs).  1e-6: ``torch.cdist`` is not bit-stable
+    across host CPUs (matmul formulation above 25 rows); on the generating host it is exact, see the live test."""
+    from oracle import ir_oracle
+    g = golden["euclidean_score"]
+    a, b = torch.tensor(g["a"]), torch.tensor(g["b"])
+    torch.testing.assert_close(ir_oracle.euclidean_score(a, b), torch.tensor(g["scores"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(ir_oracle.euclidean_score(a[0], b[1]), torch.tensor(g["one_d"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(ir_oracle.euclidean_score(a[:2].tolist(), b[:3].tolist()),
+                               torch.tensor(g["from_lists"]), rtol=1e-6, atol=1e-7)
+    assert torch.tensor(g["one_d"]).shape == (1, 1)
+
+
+@pytest.mark.skipif(not rs.available(), reason="the reference is only mounted in the authoring container")
+def test_fixture_is_what_the_reference_produces_now():
+    """Re-derives every vector from /root/reference and compares with the committed file: the fixture cannot
+    drift from the code it claims to come from."""
+    from oracle import ir_oracle
+    with open(os.path.join(HERE, "golden", "evaluators_golden.json")) as fp:
+        want = json.load(fp)
+    ns = rs.load("euclidean_score", "QuadrupletLossEvaluator", "QuadrupletEvaluator")
+    assert [gen.run_quadruplet_evaluator(ns, g) for g in gen.GAMMAS] == want["quadruplet_evaluator"]
+    got = [gen.run_loss_evaluator(ns, c["n_items"], c["batch_size"]) for c in want["loss_evaluator"]]
+    assert got == want["loss_evaluator"]
+    random.seed(14)
+    ev = ns["QuadrupletEvaluator"].from_input_examples(gen.dict_examples(), gamma=0.6, name="s")
+    assert [ev.anchors, ev.positives, ev.partially_positives, ev.negatives] == want["sampling"]["first"]
+    # the three inner evaluators are built on the sampled lists with the reference's pairing (:188-220)
+    built = {t.name: t for t in rs.ScriptedTriplet.built[-3:]}
+    assert built["pos_part"].negatives is ev.partially_positives and built["part_neg"].positives is ev.partially_positives
+    assert built["pos_neg"].positives is ev.positives and built["pos_neg"].negatives is ev.negatives
+    # euclidean_score: reference function vs oracle restatement, same host -> bit for bit
+    g = torch.Generator().manual_seed(3)
+    for shape_a, shape_b in (((5, 12), (9, 12)), ((40, 64), (70, 64)), ((1, 3), (2, 3))):
+        a, b = torch.randn(*shape_a, generator=g), torch.randn(*shape_b, generator=g)
+        assert torch.equal(ns["euclidean_score"](a, b), ir_oracle.euclidean_score(a, b))
+    assert torch.equal(ns["euclidean_score"](a[0], b), ir_oracle.euclidean_score(a[0], b))
+    assert torch.equal(ns["euclidean_score"](a.tolist(), b.tolist()), ir_oracle.euclidean_score(a.tolist(), b.tolist()))
