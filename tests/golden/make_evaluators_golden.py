@@ -9,8 +9,10 @@ Run in the authoring container only (needs /root/reference):
 third-party pieces scripted (see its docstring).  Stored here: the scripted inputs and what the reference
 code made of them -- sampled quadruplets for a seeded ``random``, return values and CSV text of
 ``QuadrupletEvaluator.__call__`` (``:345-389``), return values and JSON text of
-``QuadrupletLossEvaluator.__call__`` (``:49-128``), and ``euclidean_score`` (``:392-405``) on a small
-seeded case.  Seed 14 is the reference's RANDOM_SEED (``dataset/constants.py:5``).
+``QuadrupletLossEvaluator.__call__`` (``:49-128``), ``euclidean_score`` (``:392-405``) on a small
+seeded case, and the evaluation-set file ``create_ir_evaluation_set`` (``:406-530``) writes together with
+what its two reload paths (its own, and ``get_sequential_evaluator``'s ``:556-561``) make of it.  Seed 14 is
+the reference's RANDOM_SEED (``dataset/constants.py:5``).
 """
 import json
 import os
@@ -25,6 +27,10 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import reference_sandbox as rs  # noqa: E402
+
+
+LIFTED = ("euclidean_score", "QuadrupletLossEvaluator", "QuadrupletEvaluator", "create_ir_evaluation_set",
+          "get_sequential_evaluator")
 
 
 def dict_examples(n=12):
@@ -71,10 +77,50 @@ def run_loss_evaluator(ns, n_items, batch_size):
             "returned": [float(first), float(second)], "returned_dtype": str(first.dtype), "json_text": text}
 
 
+def list_examples(n=12):
+    """Items as create_ir_evaluation_set iterates them (:455-490): every example field is a list."""
+    out = dict_examples(n)
+    for item in out:
+        if isinstance(item["part_positive"], str):
+            item["part_positive"] = [item["part_positive"]]
+    return out
+
+
+class LossWithGamma:
+    gamma = 0.6            # get_sequential_evaluator reads loss.gamma (:593)
+
+
+def run_ir_evaluation_set(ns, use_pos, use_part_pos, add_part_pos_corpus):
+    """create_ir_evaluation_set (:406-530) on a seeded dataset, then the reload paths: its own (:414-431,
+    per-query sets) and get_sequential_evaluator's (:556-561, the set of ALL query ids for every query),
+    whose result is what the reference hands to InformationRetrievalEvaluator (:572-588)."""
+    random.seed(14)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "created_eval_queries.json")
+        made = ns["create_ir_evaluation_set"](list_examples(), n_queries=5, out_path=path, use_pos=use_pos,
+                                              use_part_pos=use_part_pos, use_cross_encoder=False,
+                                              add_part_pos_corpus=add_part_pos_corpus)
+        text = open(path).read()
+        again = ns["create_ir_evaluation_set"](list_examples(), out_path=path)          # file exists: reload branch
+        rs.RecordingEvaluator.built = []
+        ns["get_sequential_evaluator"](list_examples(), LossWithGamma(), evaluation_queries_path=path, name="val")
+        ire, seq = rs.RecordingEvaluator.built
+    assert made["queries"] == again["queries"] and made["relevant"] == again["relevant"]
+    kw = dict(ire.kwargs)
+    return {"flags": {"use_pos": use_pos, "use_part_pos": use_part_pos, "add_part_pos_corpus": add_part_pos_corpus},
+            "file_text": text,
+            "queries": made["queries"], "corpus": made["corpus"],
+            "relevant": {q: sorted(v) for q, v in made["relevant"].items()},
+            "relevant_after_sequential_evaluator_reload": {q: sorted(v) for q, v in kw["relevant_docs"].items()},
+            "ire_kwargs": {k: v for k, v in kw.items() if k not in ("queries", "corpus", "relevant_docs", "score_functions")},
+            "ire_score_function_names": sorted(kw["score_functions"]),
+            "sequential_order": [type(e).__name__ for e in seq.kwargs["evaluators"]]}
+
+
 def main():
     if not rs.available():
         raise SystemExit("/root/reference not present: golden vectors can only be made in the authoring container")
-    ns = rs.load("euclidean_score", "QuadrupletLossEvaluator", "QuadrupletEvaluator")
+    ns = rs.load(*LIFTED)
     out = {"calls": CALLS, "triplet_script": TRIPLET_SCRIPT, "batch_losses": BATCH_LOSSES}
 
     # sampling (:224-262) and the re-sampling every 5 epochs (:264-343)
@@ -89,6 +135,9 @@ def main():
 
     out["quadruplet_evaluator"] = [run_quadruplet_evaluator(ns, g) for g in GAMMAS]
     out["loss_evaluator"] = [run_loss_evaluator(ns, n, b) for n, b in ((10, 1), (10, 3), (7, 32), (64, 8))]
+
+    out["ir_evaluation_set"] = [run_ir_evaluation_set(ns, *flags) for flags in
+                                ((True, True, True), (True, False, True), (False, True, True), (True, False, False))]
 
     g = torch.Generator().manual_seed(14)
     a, b = torch.randn(5, 12, generator=g), torch.randn(9, 12, generator=g)

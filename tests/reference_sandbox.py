@@ -13,7 +13,10 @@ which only the third-party names are stand-ins:
 * ``QuadrupletSentenceTransformerLossModel`` -> ``ScriptedLossModel``: returns the per-batch loss tensors the
   test scripted (the loss arithmetic itself is pinned by ``tests/golden/loss_golden.npz``);
 * ``SentenceEvaluator`` -> ``object``, ``InputExample`` -> a two-field class, ``tqdm`` / ``autocast`` /
-  ``batch_to_device`` -> no-ops.
+  ``batch_to_device`` -> no-ops;
+* for ``create_ir_evaluation_set`` / ``get_sequential_evaluator`` (``:406-614``): sentence-transformers'
+  ``InformationRetrievalEvaluator`` / ``SequentialEvaluator`` -> ``RecordingEvaluator`` (keeps the constructor
+  arguments), ``generate_variations`` (text augmentation of the query) -> identity.
 
 Everything else the lifted code executes (sampling with ``random``, the 5-epoch re-sampling, the global
 accuracy formula, the incremental mean in tensor arithmetic, CSV and JSON writing) is the reference's.
@@ -92,6 +95,24 @@ class StubSentenceModel:
         return [batch], torch.zeros(len(batch))
 
 
+class RecordingEvaluator:
+    """Stand-in for sentence-transformers' InformationRetrievalEvaluator / SequentialEvaluator: keeps what the
+    reference's code hands to the constructor."""
+    built = []
+
+    def __init__(self, *args, **kwargs):
+        self.args, self.kwargs = args, kwargs
+        RecordingEvaluator.built.append(self)
+
+
+def cos_sim_marker(a, b):
+    raise AssertionError("stand-in for sentence_transformers.util.cos_sim: never called in the sandbox")
+
+
+def dot_score_marker(a, b):
+    raise AssertionError("stand-in for sentence_transformers.util.dot_score: never called in the sandbox")
+
+
 class _Bar:
     def __init__(self, it=None, **kw):
         self._it = it
@@ -130,10 +151,19 @@ def load(*names):
         "TripletEvaluator": ScriptedTriplet, "QuadrupletSentenceTransformerLossModel": ScriptedLossModel,
         "tqdm": _Bar, "autocast": contextlib.nullcontext, "batch_to_device": lambda batch, device: batch,
         "LOGGER": logging.getLogger("reference.models.evaluators"),
+        # create_ir_evaluation_set / get_sequential_evaluator (:406-614)
+        "Subset": torch.utils.data.Subset, "GammaQuadrupletLoss": object,
+        "InformationRetrievalEvaluator": RecordingEvaluator, "SequentialEvaluator": RecordingEvaluator,
+        "cos_sim": cos_sim_marker, "dot_score": dot_score_marker,
+        "generate_variations": lambda sentence, n=1: [sentence],      # dataset/sentence_compr_dataset_creation.py (text augmentation)
     }
     for key in ("REFERENCE_EXAMPLE", "POS_EXAMPLES", "PART_POS_EXAMPLES", "NEG_EXAMPLES", "RANDOM_SEED"):
         ns[key] = consts[key]
     tree = ast.parse(open(EVALUATORS).read())
+    # the module-level constants of the file (IR_EVALUATION_PATH, N_IR_SAMPLES, SIMILARITY_THRESHOLD)
+    consts_here = [n for n in tree.body if isinstance(n, ast.AnnAssign) and isinstance(n.target, ast.Name)
+                   and n.target.id.isupper()]
+    exec(compile(ast.Module(body=consts_here, type_ignores=[]), EVALUATORS, "exec"), ns)
     found = {n.name: n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
     for name in names:
         exec(compile(ast.Module(body=[found[name]], type_ignores=[]), EVALUATORS, "exec"), ns)

@@ -1,10 +1,10 @@
-"""The host side of SURVEY 8f row 3 (and a8) pinned to the reference's OWN code.
+"""The host side of SURVEY 8f rows 3-4 (and a8) pinned to the reference's OWN code.
 
 ``tests/golden/evaluators_golden.json`` holds what ``/root/reference/models/evaluators.py`` itself produces
 (``QuadrupletEvaluator`` sampling / global accuracy / CSV, ``QuadrupletLossEvaluator`` incremental mean / JSON
-log, ``euclidean_score``) when only its third-party collaborators are scripted -- see
-``tests/reference_sandbox.py`` and ``tests/golden/make_evaluators_golden.py``.  Here the drop-in classes and
-the oracle restatements are held against those vectors on the CPU (the device work underneath -- embeddings,
+log, ``euclidean_score``, the evaluation-set file of ``create_ir_evaluation_set`` and its reloads) when only
+its third-party collaborators are scripted -- see ``tests/reference_sandbox.py`` and
+``tests/golden/make_evaluators_golden.py``.  Here the drop-in classes and the oracle restatements are held against those vectors on the CPU (the device work underneath -- embeddings,
 the nine comparison counts, the per-batch losses -- is scripted the same way and is covered by the ``-m gpu``
 tests), and, when the reference is mounted, the fixture is re-derived from the reference and must not have
 drifted."""
@@ -128,6 +128,33 @@ def test_euclidean_score_oracle_equals_the_reference_function(golden):
     assert torch.tensor(g["one_d"]).shape == (1, 1)
 
 
+def test_evaluation_set_written_by_the_reference_loads_as_the_reference_reloads_it(golden, tmp_path):
+    """SURVEY 8f row 4.  The file is the one ``create_ir_evaluation_set`` (models/evaluators.py:406-530) wrote;
+    ``load_ir_evaluation_set`` gives the per-query sets the function itself returns and reloads (:414-431),
+    ``reference_compatible=True`` the sets ``get_sequential_evaluator`` (:556-561) and the script
+    (ir_evauation_script.py:94-96) hand to the evaluator -- every query's set = all query ids.  The keyword
+    set the reference then passes (:572-588) builds the drop-in evaluator."""
+    import qst_b200
+    fns = {"cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score}
+    for i, case in enumerate(golden["ir_evaluation_set"]):
+        path = tmp_path / f"created_eval_queries_{i}.json"
+        path.write_text(case["file_text"])
+        queries, corpus, relevant = qst_b200.load_ir_evaluation_set(str(path))
+        assert queries == case["queries"] and corpus == case["corpus"]
+        assert list(queries) == list(case["queries"]) and list(corpus) == list(case["corpus"])     # order kept
+        assert relevant == {q: set(v) for q, v in case["relevant"].items()}
+        q2, c2, literal = qst_b200.load_ir_evaluation_set(str(path), reference_compatible=True)
+        assert (q2, c2) == (queries, corpus)
+        assert literal == {q: set(v) for q, v in case["relevant_after_sequential_evaluator_reload"].items()}
+        assert all(v == set(queries) for v in literal.values())
+        ev = qst_b200.InformationRetrievalEvaluator(
+            queries=queries, corpus=corpus, relevant_docs=relevant,
+            score_functions={n: fns[n] for n in case["ire_score_function_names"]}, **case["ire_kwargs"])
+        assert ev.csv_file == "Information-Retrieval_evaluation_val_results.csv"
+        assert ev.queries_ids == [q for q in queries if relevant[q]]
+        assert case["sequential_order"][1:] == ["QuadrupletEvaluator", "QuadrupletLossEvaluator"]
+
+
 @pytest.mark.skipif(not rs.available(), reason="the reference is only mounted in the authoring container")
 def test_fixture_is_what_the_reference_produces_now():
     """Re-derives every vector from /root/reference and compares with the committed file: the fixture cannot
@@ -135,8 +162,11 @@ def test_fixture_is_what_the_reference_produces_now():
     from oracle import ir_oracle
     with open(os.path.join(HERE, "golden", "evaluators_golden.json")) as fp:
         want = json.load(fp)
-    ns = rs.load("euclidean_score", "QuadrupletLossEvaluator", "QuadrupletEvaluator")
+    ns = rs.load(*gen.LIFTED)
     assert [gen.run_quadruplet_evaluator(ns, g) for g in gen.GAMMAS] == want["quadruplet_evaluator"]
+    got = [gen.run_ir_evaluation_set(ns, *(c["flags"][k] for k in ("use_pos", "use_part_pos", "add_part_pos_corpus")))
+           for c in want["ir_evaluation_set"]]
+    assert got == want["ir_evaluation_set"]
     got = [gen.run_loss_evaluator(ns, c["n_items"], c["batch_size"]) for c in want["loss_evaluator"]]
     assert got == want["loss_evaluator"]
     random.seed(14)
