@@ -780,8 +780,7 @@ def f2_config1(dev):
     from oracle import ir_oracle
     q, c, queries, corpus, relevant = qst_b200.synth.ir_eval_set(1000, 10_000, 384)
     table = torch.cat([q, c])
-    kl = [1, 3, 5, 10, 20, 50, 100, 200, 500, 900]
-    kw = dict(mrr_at_k=kl, ndcg_at_k=kl, accuracy_at_k=kl, precision_recall_at_k=kl, map_at_k=kl, write_csv=False)
+    kw = dict(qst_b200.synth.SCRIPT_DEFAULT_K_LISTS, write_csv=False)
     ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
         "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score}, **kw)
     model = qst_b200.synth.TableModel(table.to(dev))

@@ -13,6 +13,15 @@ import torch
 SEED = 14
 
 
+# argparse defaults of the reference's evaluation script (``/root/reference/ir_evauation_script.py:163-173``):
+# MRR / NDCG at ten cut-offs, Accuracy / Precision-Recall / MAP at twelve, the largest 900.  Held against the
+# script's source by tests/test_host_logic.py::test_script_default_k_lists_are_the_reference_scripts.
+_K10 = [5, 10, 20, 30, 40, 50, 100, 200, 500, 900]
+_K12 = [1, 3] + _K10
+SCRIPT_DEFAULT_K_LISTS = {"mrr_at_k": _K10, "ndcg_at_k": _K10, "accuracy_at_k": _K12,
+                          "precision_recall_at_k": _K12, "map_at_k": _K12}
+
+
 def _gen(i: int) -> torch.Generator:
     return torch.Generator().manual_seed(SEED + i)
 

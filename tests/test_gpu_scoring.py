@@ -577,8 +577,7 @@ def test_evaluator_csv_is_byte_identical_to_the_reference_writer(tmp_path):
     from oracle import ir_oracle
     q, c, queries, corpus, relevant = qst_b200.synth.ir_eval_set(300, 4000, 96)
     table = torch.cat([q, c])
-    kl = [1, 3, 5, 10, 20, 50, 100, 200, 500, 900]
-    kw = dict(mrr_at_k=kl, ndcg_at_k=kl, accuracy_at_k=kl, precision_recall_at_k=kl, map_at_k=kl, name="val")
+    kw = dict(qst_b200.synth.SCRIPT_DEFAULT_K_LISTS, name="val")
     ev = qst_b200.InformationRetrievalEvaluator(queries, corpus, relevant, score_functions={
         "cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score}, **kw)
     ref = ir_oracle.InformationRetrievalEvaluatorOracle(queries, corpus, relevant, score_functions={

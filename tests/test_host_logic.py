@@ -379,3 +379,40 @@ def test_evaluator_signatures_match_the_reference_definitions():
     for cls in ("QuadrupletEvaluator", "QuadrupletLossEvaluator"):
         for method in ("__init__", "__call__"):
             same(ref_params(classes[cls][method]), ours(getattr(getattr(qst_b200, cls), method)), f"{cls}.{method}")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="the reference is only mounted in the authoring container")
+def test_script_default_k_lists_are_the_reference_scripts():
+    """``synth.SCRIPT_DEFAULT_K_LISTS`` (what bench.py's f2_config1 and the CSV test call "the script
+    defaults") against the argparse defaults in the source of ir_evauation_script.py:163-183; the drop-in
+    evaluator built with them has the script's 900 as max_k and 2 + 3 * 68 CSV columns."""
+    import ast
+
+    import qst_b200
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "ir_evauation_script.py")).read())
+    defaults = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", None) == "add_argument" and node.args:
+            flag = ast.literal_eval(node.args[0])
+            for kw in node.keywords:
+                if kw.arg == "default":
+                    try:
+                        defaults[flag.lstrip("-")] = ast.literal_eval(kw.value)
+                    except ValueError:
+                        pass
+    for name, ks in qst_b200.synth.SCRIPT_DEFAULT_K_LISTS.items():
+        assert defaults[name] == ks, name
+    assert defaults["corpus_chunk_size"] == 50000 and defaults["write_csv"] is True and defaults["batch_size"] == 32
+    assert defaults["score_functions"] == "all" and defaults["main_score_function"] is None
+    # the score-function table of the script (:70): same three names the drop-in recognises
+    table = [n for n in ast.walk(tree) if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "score_functions"
+             and isinstance(n.value, ast.Dict)]
+    names = [ast.literal_eval(k) for k in table[0].value.keys]
+    assert names == ["cos_sim", "dot_score", "euclid_score"]
+    fns = {"cos_sim": qst_b200.cos_sim, "dot_score": qst_b200.dot_score, "euclid_score": qst_b200.euclidean_score}
+    ev = qst_b200.InformationRetrievalEvaluator({"q": "0"}, {"d": "1"}, {"q": {"d"}}, score_functions=fns,
+                                                corpus_chunk_size=defaults["corpus_chunk_size"],
+                                                write_csv=defaults["write_csv"], batch_size=defaults["batch_size"],
+                                                main_score_function=defaults["main_score_function"],
+                                                **qst_b200.synth.SCRIPT_DEFAULT_K_LISTS)
+    assert ev.max_k == 900 and len(ev.csv_headers) == 2 + 3 * (12 + 2 * 12 + 10 + 10 + 12)
