@@ -416,3 +416,17 @@ def test_script_default_k_lists_are_the_reference_scripts():
                                                 main_score_function=defaults["main_score_function"],
                                                 **qst_b200.synth.SCRIPT_DEFAULT_K_LISTS)
     assert ev.max_k == 900 and len(ev.csv_headers) == 2 + 3 * (12 + 2 * 12 + 10 + 10 + 12)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="the reference is only mounted in the authoring container")
+def test_dissimilar_mask_defaults_to_the_reference_threshold():
+    """dataset/quadruplet_dataset.py:20, 233: candidates with ``cos_score <= NEG_EXAMPLE_SIM_TRESHOLD`` survive."""
+    import ast
+    import inspect
+
+    import qst_b200
+    src = open(os.path.join(REFERENCE_ROOT, "dataset", "quadruplet_dataset.py")).read()
+    consts = {n.target.id: ast.literal_eval(n.value) for n in ast.parse(src).body
+              if isinstance(n, ast.AnnAssign) and isinstance(n.target, ast.Name) and n.target.id == "NEG_EXAMPLE_SIM_TRESHOLD"}
+    assert inspect.signature(qst_b200.dissimilar_mask).parameters["threshold"].default == consts["NEG_EXAMPLE_SIM_TRESHOLD"]
+    assert "cos_scores <= NEG_EXAMPLE_SIM_TRESHOLD" in src                      # `<=`, not `<` (the mask is inclusive)
