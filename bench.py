@@ -33,7 +33,8 @@ scores back (two small all-to-alls); thresholds are shared between shards throug
   secondary  loss_config2 (N = 1); f2_config1 (N = 1: the whole evaluator call, k up to 900, three score
              functions); replicated_master, config4 (100k x 10M) for N >= 2; config5 (1M x 1M + metrics)
              for N = 8
-`--impl reference` times only the CPU path and prints it in the same format.
+`--impl reference` times only the CPU path and prints it in the same format, with the same `metric`, `unit` and
+`config.workload` (what differs between the arms is in `config.implementation`).
 """
 from __future__ import annotations
 
@@ -60,6 +61,10 @@ CPU_SAMPLE_Q = 1000
 SLAB = 125_000            # the synthetic corpus is generated slab by slab, slab i from seed CORPUS_SEED + i
 CORPUS_SEED = 14 + 1000
 PARITY_SAMPLE = 256
+# the workload both arms (`--impl ours` / `--impl reference`) name in config.workload: BASELINE.json configs[2],
+# weak scaling (every GPU brings Q_PER_GPU queries; the corpus is sharded over the GPUs)
+WORKLOAD = (f"config 3: cos_sim + exact top-{TOPK}, {Q_PER_GPU} queries per GPU x {N_CORPUS} corpus rows x {DIM}-d "
+            f"fp32 embeddings (synthetic N(0,1), seed {CORPUS_SEED})")
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -311,8 +316,9 @@ def run_reference(args):
         "unit": "queries/s", "n_gpus": args.gpus, "steps": base["steps"], "warmup": base["warmup"],
         "ms_per_step": base["ms_per_sample_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cos_sim + top-{TOPK}: queries x {N_CORPUS} corpus x {DIM}-d on the host CPUs "
-                               f"(a step = {CPU_SAMPLE_Q} queries, see cpu_baseline.sample)"},
+        "config": {"workload": WORKLOAD,
+                   "implementation": f"the reference's path restated (oracle port) on the host CPUs; a step = "
+                                     f"{CPU_SAMPLE_Q} queries against the full corpus, see cpu_baseline.sample"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -610,10 +616,11 @@ def run_ours(args):
         "value": Q / (ms_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"cos_sim + top-{TOPK}: {Q} queries x {N_CORPUS} corpus x {DIM}-d, fp32 masters, "
-                               f"bf16 tensor-core first pass k'={plan.kprime}, fp32 rescore; corpus sharded over {world} "
-                               f"GPU(s): bf16 operand AND fp32 master of a rank's own rows only, exact scores of "
-                               f"requested rows returned to the owner of a query; {Q_PER_GPU} queries per GPU per step",
+        "config": {"workload": WORKLOAD,
+                   "implementation": f"{Q} queries x {N_CORPUS} corpus x {DIM}-d, fp32 masters, "
+                                     f"bf16 tensor-core first pass k'={plan.kprime}, fp32 rescore; corpus sharded over {world} "
+                                     f"GPU(s): bf16 operand AND fp32 master of a rank's own rows only, exact scores of "
+                                     f"requested rows returned to the owner of a query; {Q_PER_GPU} queries per GPU per step",
                    "l2": "inputs larger than L2 (bf16 corpus shard %.2f GB + fp32 masters)" % (index.n * DIM * 2 / 1e9),
                    "plan": {"m_tiles": plan.m_tiles, "n_tiles": plan.n_tiles, "stripes": plan.stripes,
                             "units": plan.units, "grid": plan.grid, "query_stationary": int(plan.qs)},
