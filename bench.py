@@ -625,8 +625,13 @@ def run_ours(args):
                    "plan": {"m_tiles": plan.m_tiles, "n_tiles": plan.n_tiles, "stripes": plan.stripes,
                             "units": plan.units, "grid": plan.grid, "query_stationary": int(plan.qs)},
                    "uncertified_queries_after_first_pass_and_rescan": uncertified},
-        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "mode": e2e_mode,
+        # both host-buffer entries are timed with their copies inside the timed region; the headline is the
+        # faster of the two (normally the double-buffered stream; at N = 2 the pipeline has been seen to
+        # fall behind the plain call on some boxes), both numbers are kept
+        "e2e": {"value": Q / (min(ms_e2e, ms_e2e_serial) * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": min(ms_e2e, ms_e2e_serial),
+                "mode": e2e_mode if ms_e2e <= ms_e2e_serial else "one synchronous host-buffer call per step",
+                "pipelined_value": Q / (ms_e2e * 1e-3), "pipelined_ms_per_step": ms_e2e,
                 "serial_call_value": Q / (ms_e2e_serial * 1e-3), "serial_call_ms_per_step": ms_e2e_serial,
                 "pipelined_ranking_identical_to_serial": pipe_same},
         # counted by the library (qst_launch_count) around the timed region, on rank 0
