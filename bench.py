@@ -18,9 +18,9 @@ scores back (two small all-to-alls); thresholds are shared between shards throug
 
   value      inputs resident in HBM, CUDA-event time on the launching stream
   e2e        the same step through the host-buffer entry: pinned host queries are copied in and the
-             ranking is copied back inside the timed region, every step, double-buffered
-             (`qst_b200.HostTopkPipeline` / `qst_b200.sharded.ShardedHostPipeline`), with the
-             one-synchronous-call-per-step number beside it
+             ranking is copied back inside the timed region, every step: double-buffered
+             (`qst_b200.HostTopkPipeline` / `qst_b200.sharded.ShardedHostPipeline`) and as one synchronous
+             call per step; `value` is the faster of the two (`mode` says which), both are kept
   roofline   dominant kernel (K2): 2*Q*N*D FLOP per launch / its mean duration inside the steps, against
              the measured sustained bf16 peak of MEASURED_PEAKS.json
   parity_sample  >= 256 queries of the timed batch re-computed with plain torch fp32
