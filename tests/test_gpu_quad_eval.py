@@ -126,3 +126,48 @@ def test_dissimilar_mask_matches_cos_sim_threshold():
     sure = (want - 0.2).abs() > 1e-5
     assert torch.equal(mask.cpu()[sure], (want <= 0.2)[sure])
     assert int(mask.sum()) >= 35 and not bool(mask[:10].any())
+
+
+def test_device_paths_against_the_reference_codes_recorded_outputs(tmp_path):
+    """tests/golden/evaluators_golden.json holds what the reference's OWN code produced
+    (tests/golden/make_evaluators_golden.py): ``euclidean_score`` of models/evaluators.py:392-405 on a seeded
+    case, and the incremental mean of ``QuadrupletLossEvaluator`` (:84-98) over scripted batch losses.  Here
+    the device paths: the drop-in's ``euclidean_score`` (K3 arithmetic) against the recorded matrix, and the
+    drop-in ``QuadrupletLossEvaluator`` run end to end on the GPU with a loss module that returns the scripted
+    values -- same running mean, same JSON log."""
+    import json
+    import qst_b200
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "evaluators_golden.json")) as fp:
+        golden = json.load(fp)
+    g = golden["euclidean_score"]
+    a, b = torch.tensor(g["a"]), torch.tensor(g["b"])
+    got = qst_b200.euclidean_score(a.to(_dev()), b.to(_dev())).cpu()
+    torch.testing.assert_close(got, torch.tensor(g["scores"]), rtol=1e-5, atol=1e-6)     # cdist vs direct (q-c)^2 sums
+    one = qst_b200.euclidean_score(a[0].to(_dev()), b[1].to(_dev())).cpu()
+    torch.testing.assert_close(one, torch.tensor(g["one_d"]), rtol=1e-5, atol=1e-6)
+
+    class ScriptedLoss(torch.nn.Module):
+        """Returns the scripted batch losses as device scalars (the fused loss itself has its own tests)."""
+
+        def __init__(self, values):
+            super().__init__()
+            self.values = list(values)
+
+        def forward(self, x_anchor, x_pos, x_part, x_neg, **kw):
+            assert x_anchor.is_cuda and x_anchor.shape == x_neg.shape
+            return torch.tensor(self.values.pop(0), dtype=torch.float32, device=x_anchor.device)
+
+    table = torch.randn(64, 16, generator=torch.Generator().manual_seed(5)).to(_dev())
+    model = qst_b200.synth.TableModel(table)
+    for case in golden["loss_evaluator"]:
+        n_batches = len(case["batch_sizes_seen"])
+        losses = golden["batch_losses"][:n_batches]
+        items = [(str(i % 64), str((i + 1) % 64), str((i + 2) % 64), str((i + 3) % 64)) for i in range(case["n_items"])]
+        out = tmp_path / f"{case['n_items']}_{case['batch_size']}"
+        out.mkdir()
+        loss = ScriptedLoss(losses + losses[::-1])
+        ev = qst_b200.QuadrupletLossEvaluator(items, loss, batch_size=case["batch_size"])
+        first = ev(model, output_path=str(out), epoch=0, steps=-1)
+        second = ev(model, output_path=str(out), epoch=1, steps=40)
+        assert [first, second] == case["returned"]
+        assert open(out / "_quadruplet_loss_eval.json").read() == case["json_text"]
