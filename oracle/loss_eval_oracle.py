@@ -4,6 +4,10 @@ Restates ``/root/reference/models/evaluators.py:84-98``: per-batch loss values (
 ``oracle.loss_oracle``) folded with ``average_loss = average_loss + 1 / (i + 1) * (loss_value -
 average_loss)`` in torch tensor arithmetic, starting from the Python float 0.0.  The expression is
 the reference's own; the loss values under it are pinned by ``tests/golden/loss_golden.npz``.
+PINNED as a whole: ``evaluate`` equals, bit for bit, what the reference's un-scripted stack (its
+``QuadrupletLossEvaluator``, its ``QuadrupletSentenceTransformerLossModel``, its ``GammaQuadrupletLoss``) returns
+for a table-lookup sentence model (``tests/test_reference_evaluators.py``, fixture ``full_loss_stack`` of
+``tests/golden/evaluators_golden.json``).
 """
 import torch
 

@@ -117,6 +117,32 @@ def run_ir_evaluation_set(ns, use_pos, use_part_pos, add_part_pos_corpus):
             "sequential_order": [type(e).__name__ for e in seq.kwargs["evaluators"]]}
 
 
+FULL_STACK_CASES = [   # (loss kwargs, batch size) for the un-scripted run below
+    (dict(gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5), 16),
+    (dict(gamma=0.3, margin_pos_neg=0.7, margin_pos_part=0.2, margin_part_neg=0.9, p=1.0, swap=True, reduction="sum"), 32),
+    (dict(gamma=1.0, margin_pos_neg=0.1, margin_pos_part=2.0, margin_part_neg=0.5, p=3.0), 7),
+]
+
+
+def full_stack_table(n=70, d=48):
+    g = torch.Generator().manual_seed(14)
+    return n, torch.randn(4 * n, d, generator=g)
+
+
+def run_full_loss_stack(loss_kwargs, batch_size):
+    """Nothing scripted: the reference's QuadrupletLossEvaluator (:34-128) drives the reference's
+    QuadrupletSentenceTransformerLossModel (models/quadruplet_sentence_transformer.py:9-78) and the reference's
+    GammaQuadrupletLoss (models/losses/losses.py:241-303) over a table-lookup sentence model on the CPU."""
+    from oracle import loss_oracle
+    ns = rs.load("QuadrupletLossEvaluator", real_loss_model=True)
+    n, table = full_stack_table()
+    items = [(i, n + i, 2 * n + i, 3 * n + i) for i in range(n)]
+    loss = loss_oracle.load_reference_losses().GammaQuadrupletLoss(**loss_kwargs)
+    ev = ns["QuadrupletLossEvaluator"](items, loss, batch_size=batch_size)
+    with tempfile.TemporaryDirectory() as tmp:
+        return ev(rs.TableSentenceModel(table), output_path=tmp, epoch=0, steps=0)
+
+
 def main():
     if not rs.available():
         raise SystemExit("/root/reference not present: golden vectors can only be made in the authoring container")
@@ -138,6 +164,9 @@ def main():
 
     out["ir_evaluation_set"] = [run_ir_evaluation_set(ns, *flags) for flags in
                                 ((True, True, True), (True, False, True), (False, True, True), (True, False, False))]
+
+    out["full_loss_stack"] = [{"loss_kwargs": kw, "batch_size": bs, "average_loss": float(run_full_loss_stack(kw, bs))}
+                              for kw, bs in FULL_STACK_CASES]
 
     g = torch.Generator().manual_seed(14)
     a, b = torch.randn(5, 12, generator=g), torch.randn(9, 12, generator=g)

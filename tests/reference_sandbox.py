@@ -18,6 +18,11 @@ which only the third-party names are stand-ins:
   ``InformationRetrievalEvaluator`` / ``SequentialEvaluator`` -> ``RecordingEvaluator`` (keeps the constructor
   arguments), ``generate_variations`` (text augmentation of the query) -> identity.
 
+``load(..., real_loss_model=True)`` puts the reference's own ``QuadrupletSentenceTransformerLossModel`` (lifted
+from models/quadruplet_sentence_transformer.py the same way) in place of ``ScriptedLossModel``; with the
+reference's loss module and ``TableSentenceModel`` (texts = rows of an embedding table) nothing on the loss
+side is scripted any more.
+
 Everything else the lifted code executes (sampling with ``random``, the 5-epoch re-sampling, the global
 accuracy formula, the incremental mean in tensor arithmetic, CSV and JSON writing) is the reference's.
 """
@@ -138,8 +143,43 @@ def _constants():
     return ns
 
 
-def load(*names):
-    """Namespace in which the named top-level definitions of models/evaluators.py have been executed."""
+LOSS_MODEL = os.path.join(REFERENCE_ROOT, "models", "quadruplet_sentence_transformer.py")
+
+
+def load_loss_model():
+    """The reference's ``QuadrupletSentenceTransformerLossModel`` (models/quadruplet_sentence_transformer.py:9-78):
+    runs the sentence model on the four texts of a batch and calls the quadruplet loss with keywords."""
+    consts = _constants()
+    ns = {"torch": torch, "random": random, "Tuple": typing.Tuple, "Any": typing.Any, "Optional": typing.Optional,
+          "List": typing.List, "Dict": typing.Dict, "Union": typing.Union, "SentenceTransformer": object,
+          "InputExample": InputExample, "QuadrupletLoss": object}
+    for key in ("REFERENCE_EXAMPLE", "POS_EXAMPLES", "PART_POS_EXAMPLES", "NEG_EXAMPLES"):
+        ns[key] = consts[key]
+    tree = ast.parse(open(LOSS_MODEL).read())
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "QuadrupletSentenceTransformerLossModel")
+    exec(compile(ast.Module(body=[node], type_ignores=[]), LOSS_MODEL, "exec"), ns)
+    return ns["QuadrupletSentenceTransformerLossModel"]
+
+
+class TableSentenceModel:
+    """Stand-in for a SentenceTransformer whose 'texts' are row ids of an embedding table: what the lifted
+    QuadrupletLossEvaluator and loss model touch (``device``, ``smart_batching_collate``, ``__call__`` ->
+    ``{'sentence_embedding': ...}``).  Dataset items are 4-tuples of row ids."""
+
+    def __init__(self, table: torch.Tensor):
+        self.table, self.device = table, table.device
+
+    def smart_batching_collate(self, batch):
+        cols = list(zip(*batch))
+        return [torch.tensor(c, dtype=torch.long) for c in cols], torch.zeros(len(batch))
+
+    def __call__(self, features, **kwargs):
+        return {"sentence_embedding": self.table[features]}
+
+
+def load(*names, real_loss_model: bool = False):
+    """Namespace in which the named top-level definitions of models/evaluators.py have been executed.
+    ``real_loss_model``: the reference's own loss-model wrapper instead of ``ScriptedLossModel``."""
     consts = _constants()
     ns = {
         "csv": csv, "json": json, "logging": logging, "os": os, "random": random, "np": np, "torch": torch,
@@ -159,6 +199,8 @@ def load(*names):
     }
     for key in ("REFERENCE_EXAMPLE", "POS_EXAMPLES", "PART_POS_EXAMPLES", "NEG_EXAMPLES", "RANDOM_SEED"):
         ns[key] = consts[key]
+    if real_loss_model:
+        ns["QuadrupletSentenceTransformerLossModel"] = load_loss_model()
     tree = ast.parse(open(EVALUATORS).read())
     # the module-level constants of the file (IR_EVALUATION_PATH, N_IR_SAMPLES, SIMILARITY_THRESHOLD)
     consts_here = [n for n in tree.body if isinstance(n, ast.AnnAssign) and isinstance(n.target, ast.Name)

@@ -155,6 +155,19 @@ def test_evaluation_set_written_by_the_reference_loads_as_the_reference_reloads_
         assert case["sequential_order"][1:] == ["QuadrupletEvaluator", "QuadrupletLossEvaluator"]
 
 
+def test_loss_evaluator_oracle_equals_the_reference_full_stack(golden):
+    """``loss_eval_oracle.evaluate`` -- what the GPU test holds the drop-in ``QuadrupletLossEvaluator`` against --
+    compared with the recorded result of the reference's complete, un-scripted stack (its evaluator, its
+    loss-model wrapper, its loss module) on the same table-lookup model.  1e-6 relative across host CPUs; bit
+    for bit on the host that runs the reference (live test below)."""
+    from oracle import loss_eval_oracle
+    n, table = gen.full_stack_table()
+    a, p, pp, neg = table[:n], table[n:2 * n], table[2 * n:3 * n], table[3 * n:]
+    for case in golden["full_loss_stack"]:
+        got, _ = loss_eval_oracle.evaluate(a, p, pp, neg, case["batch_size"], **case["loss_kwargs"])
+        assert float(got) == pytest.approx(case["average_loss"], rel=1e-6)
+
+
 @pytest.mark.skipif(not rs.available(), reason="the reference is only mounted in the authoring container")
 def test_fixture_is_what_the_reference_produces_now():
     """Re-derives every vector from /root/reference and compares with the committed file: the fixture cannot
@@ -169,6 +182,14 @@ def test_fixture_is_what_the_reference_produces_now():
     assert got == want["ir_evaluation_set"]
     got = [gen.run_loss_evaluator(ns, c["n_items"], c["batch_size"]) for c in want["loss_evaluator"]]
     assert got == want["loss_evaluator"]
+    # the un-scripted loss stack: the reference's evaluator + loss-model wrapper + loss module == the oracle
+    from oracle import loss_eval_oracle
+    n, table = gen.full_stack_table()
+    for (kw, bs), rec in zip(gen.FULL_STACK_CASES, want["full_loss_stack"]):
+        theirs = gen.run_full_loss_stack(kw, bs)
+        ours, _ = loss_eval_oracle.evaluate(table[:n], table[n:2 * n], table[2 * n:3 * n], table[3 * n:], bs, **kw)
+        assert theirs.dtype == torch.float32 and torch.equal(theirs, ours)
+        assert float(theirs) == rec["average_loss"] and rec["loss_kwargs"] == kw and rec["batch_size"] == bs
     random.seed(14)
     ev = ns["QuadrupletEvaluator"].from_input_examples(gen.dict_examples(), gamma=0.6, name="s")
     assert [ev.anchors, ev.positives, ev.partially_positives, ev.negatives] == want["sampling"]["first"]
