@@ -220,6 +220,22 @@ def test_plan_picks_tile_shape_and_stripes_for_small_batches(lib):
     assert plan.kunit == 16 and plan.cap == 256
 
 
+def test_header_is_c99_and_a_plain_c_program_links_and_runs(lib, tmp_path):
+    """The boundary from the C side: ``tests/c_abi_probe.c`` is compiled as C99 (-pedantic: the header must
+    not need C++), linked against the in-tree libqst.so alone, and run here -- host-only entries (version,
+    planner, error channel, argument validation) need no device."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    libdir = os.path.join(ROOT, "quadruplet-sentence-transformer_b200")
+    exe = str(tmp_path / "c_abi_probe")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(here, "c_abi_probe.c"), "-L", libdir, "-lqst", "-Wl,-rpath," + libdir, "-o", exe],
+                   check=True, capture_output=True, text=True)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "c_abi_probe ok" in run.stdout
+
+
 def test_struct_layouts():
     import qst_b200
     assert C.sizeof(qst_b200._lib.QuadParams) == 32
