@@ -236,6 +236,22 @@ def test_header_is_c99_and_a_plain_c_program_links_and_runs(lib, tmp_path):
     assert "c_abi_probe ok" in run.stdout
 
 
+def test_integration_md_binding_stub_loads_against_the_built_library(lib):
+    """The ctypes stub INTEGRATION.md shows a maintainer (section B) is executed as written, with only the
+    library path pointed at the in-tree build: it must bind real symbols with the header's arity."""
+    import qst_b200
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if 'C.CDLL("libqst.so")' in b)
+    ns = {}
+    exec(compile(stub.replace('C.CDLL("libqst.so")', f"C.CDLL({qst_b200._lib.LIB_PATH!r})"), "INTEGRATION.md", "exec"), ns)
+    assert C.sizeof(ns["QuadParams"]) == C.sizeof(qst_b200._lib.QuadParams) == 32
+    assert [f[0] for f in ns["QuadParams"]._fields_] == [f[0] for f in qst_b200._lib.QuadParams._fields_]
+    assert len(ns["_lib"].qst_quadruplet_fwd_bwd.argtypes) == len(qst_b200._lib.SIGNATURES["qst_quadruplet_fwd_bwd"][1])
+    assert ns["_lib"].qst_quadruplet_workspace_bytes() == lib.qst_quadruplet_workspace_bytes() > 0
+    assert callable(ns["fused_loss_and_grads"])
+
+
 def test_struct_layouts():
     import qst_b200
     assert C.sizeof(qst_b200._lib.QuadParams) == 32
