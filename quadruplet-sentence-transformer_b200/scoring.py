@@ -55,9 +55,24 @@ dot_score.qst_score = "dot_score"
 euclidean_score.qst_score = "euclid_score"
 
 
+# The three callables the reference's unmodified code hands over (``ir_evauation_script.py:8-16, 70``,
+# ``models/evaluators.py:9-12, 545``): sentence-transformers' ``util.cos_sim`` / ``util.dot_score`` and the
+# reference's own ``models.evaluators.euclidean_score``.  Their arithmetic is known, so they select the fused
+# path like this package's own markers -- the evaluator drops in without touching the score-function table.
+_KNOWN_SCORE_FUNCTIONS = {("sentence_transformers.util", "cos_sim"): "cos_sim",
+                          ("sentence_transformers.util", "dot_score"): "dot_score",
+                          ("models.evaluators", "euclidean_score"): "euclid_score"}
+
+
 def score_name_of(fn) -> Optional[str]:
     """Name of the fused score function behind a callable, or None for a foreign callable."""
-    return getattr(fn, "qst_score", None)
+    name = getattr(fn, "qst_score", None)
+    if name is not None:
+        return name
+    module, fname = getattr(fn, "__module__", None), getattr(fn, "__name__", None)
+    if isinstance(module, str) and module.startswith("sentence_transformers.util"):
+        module = "sentence_transformers.util"          # later releases moved the functions into a sub-module
+    return _KNOWN_SCORE_FUNCTIONS.get((module, fname))
 
 
 def _as_2d_cuda(x) -> torch.Tensor:
