@@ -117,6 +117,8 @@ class QuadrupletEvaluator:
         self._all_examples = all_examples
         self.main_distance_function = normalize_similarity_function(main_distance_function)
         self.batch_size = batch_size
+        if show_progress_bar is None:     # models/evaluators.py:179-183: follow the logger's level
+            show_progress_bar = logger.getEffectiveLevel() in (logging.INFO, logging.DEBUG)
         self.show_progress_bar = bool(show_progress_bar)
         self.write_csv = write_csv
         self.csv_file = "quadruplet_evaluation" + ("_" + name if name else "") + "_results.csv"
