@@ -90,9 +90,14 @@ def load_reference_losses(path: str = REFERENCE_LOSSES_PATH):
     """
     if not os.path.isfile(path):
         return None
+    import sys
     spec = importlib.util.spec_from_file_location("_reference_losses", path)
     mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    keep, sys.dont_write_bytecode = sys.dont_write_bytecode, True      # never leave a __pycache__ in /root/reference
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.dont_write_bytecode = keep
     return mod
 
 

@@ -27,6 +27,7 @@ from unittest import mock
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFERENCE_ROOT = "/root/reference"
 sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True         # the reference's modules are imported from where they lie: leave no __pycache__ there
 
 import torch  # noqa: E402
 
