@@ -106,3 +106,20 @@ def test_product_validation_messages_equal_the_reference_module_live():
     for attr, val in (("margin_part_neg", 0.25), ("reduction", "sum"), ("gamma", 1.0), ("p", 3.0), ("swap", True)):
         setattr(theirs, attr, val), setattr(ours, attr, val)
         assert getattr(theirs, attr) == getattr(ours, attr) == val
+
+
+@pytest.mark.skipif(not os.path.exists(lo.REFERENCE_LOSSES_PATH), reason="the reference is only mounted in the authoring container")
+def test_loss_fixture_is_what_the_reference_produces_now(loss_golden):
+    """Every stored output and gradient of tests/golden/loss_golden.npz re-derived from the reference module
+    itself (functional form; the module form is asserted equal by the generator): the fixture the GPU tests
+    are held against cannot have drifted from the code it claims to come from.  Outputs bit for bit;
+    gradients to 1e-6 (autograd's accumulation order is torch's, not ours)."""
+    ref = lo.load_reference_losses()
+    z, cases = loss_golden
+    for c in cases:
+        leaves = [x.clone().requires_grad_(True) for x in _case_inputs(z, c)]
+        out = ref.gamma_quadruplet_loss(*leaves, **_kw(c))
+        out.sum().backward()
+        np.testing.assert_array_equal(out.detach().numpy(), z[f"{c['key']}_out"], err_msg=str(c))
+        for n, leaf in zip(("a", "p", "pp", "n"), leaves):
+            np.testing.assert_allclose(leaf.grad.numpy(), z[f"{c['key']}_g_{n}"], rtol=1e-6, atol=1e-7, err_msg=str(c))
