@@ -11,6 +11,8 @@ up to the first ``evaluator(model=..., output_path=...)``, where the drop-in ask
 no CPU fallback; on a GPU box the same call is what tests/test_gpu_scoring.py exercises).  Stand-ins beyond
 sentence-transformers: the dataset class (needs the COCO chunk files) and the packages the reference imports
 for dataset creation (nlpaug, nltk, openai, sortedcollections, torchvision), none of them on the path.
+``--oracle``: the CPU oracle's evaluator and score functions stand in instead of the drop-in's; the script then
+runs to completion on the CPU (the oracle restatement must offer everything the script asks of ST 2.2.2).
 Prints one JSON line prefixed with ``RESULT ``."""
 import ast
 import importlib
@@ -52,13 +54,27 @@ class _DatasetCreationStubs(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
 
 class SentenceTransformer:
-    """Stand-in sentence model: host embeddings, so the drop-in stops at its device check."""
+    """Stand-in sentence model with HOST embeddings (the drop-in stops at its device check; the oracle
+    evaluator runs through): "anchor i" is a seeded Gaussian row, "pos i.j" / "part i.j" lie at 1.0 / 2.0 noise
+    from it, "neg i.j" anywhere; two model names give two different tables."""
+    DIM = 32
 
     def __init__(self, name, device=None):
         self.name, self.device = name, device
+        self.salt = sum(ord(ch) for ch in name)
+
+    def _row(self, text):
+        kind, rest = text.split(" ", 1)
+        i = int(rest.split(".")[0])
+        base = torch.randn(self.DIM, generator=torch.Generator().manual_seed(1000 * self.salt + i))
+        if kind == "anchor":
+            return base
+        noise = torch.randn(self.DIM, generator=torch.Generator().manual_seed(
+            7_000_000 + 1000 * self.salt + sum(ord(ch) * (n + 1) for n, ch in enumerate(text))))
+        return {"pos": base + 1.0 * noise, "part": base + 2.0 * noise, "neg": 1.5 * noise}[kind]
 
     def encode(self, sentences, **kw):
-        return torch.zeros(len(sentences), 8)
+        return torch.stack([self._row(t) for t in sentences]) if len(sentences) else torch.zeros(0, self.DIM)
 
 
 class InputExample:
@@ -76,7 +92,9 @@ class SequentialEvaluator:
         self.evaluators = evaluators
 
 
-def install_sentence_transformers_shim():
+def install_sentence_transformers_shim(use_oracle: bool = False):
+    """``use_oracle``: the CPU oracle's evaluator and score functions instead of the drop-in's (same script, run
+    to completion on the CPU)."""
     st = types.ModuleType("sentence_transformers")
     st.__path__ = []
     ev = types.ModuleType("sentence_transformers.evaluation")
@@ -87,6 +105,10 @@ def install_sentence_transformers_shim():
     ev.SimilarityFunction = qst_b200.SimilarityFunction
     ev.InformationRetrievalEvaluator = qst_b200.InformationRetrievalEvaluator          # <- the swap
     ut.cos_sim, ut.dot_score = qst_b200.cos_sim, qst_b200.dot_score                    # <- the swap
+    if use_oracle:
+        from oracle import ir_oracle
+        ev.InformationRetrievalEvaluator = ir_oracle.InformationRetrievalEvaluatorOracle
+        ut.cos_sim, ut.dot_score = ir_oracle.cos_sim, ir_oracle.dot_score
     ut.batch_to_device = lambda batch, device: batch
     sys.modules.update({"sentence_transformers": st, "sentence_transformers.evaluation": ev,
                         "sentence_transformers.util": ut})
@@ -109,8 +131,9 @@ class FakeQuadrupletDataset:
 
 
 def main():
+    use_oracle = "--oracle" in sys.argv[1:]
     sys.meta_path.insert(0, _DatasetCreationStubs())
-    install_sentence_transformers_shim()
+    install_sentence_transformers_shim(use_oracle)
     sys.path.insert(0, REFERENCE_ROOT)
     script = importlib.import_module("ir_evauation_script")            # the reference's file, as it is
     import models.evaluators as reference_evaluators                   # noqa: E402  (the reference's module)
@@ -119,10 +142,15 @@ def main():
 
     built = []
 
-    class Recording(qst_b200.InformationRetrievalEvaluator):
+    class Recording(script.InformationRetrievalEvaluator):
         def __init__(self, *a, **k):
             super().__init__(*a, **k)
             built.append((self, k))
+            self.returned = []
+
+        def __call__(self, *a, **k):
+            self.returned.append(super().__call__(*a, **k))
+            return self.returned[-1]
 
     script.InformationRetrievalEvaluator = Recording
 
@@ -149,7 +177,13 @@ def main():
         except Exception as e:  # noqa: BLE001
             result["stopped_at"] = [type(e).__name__, str(e)]
         written = sorted(f for _, _, files in os.walk(os.path.join(tmp, "out")) for f in files)
+        csv_text = None
+        for folder, _, files in os.walk(os.path.join(tmp, "out")):
+            for f in files:
+                if f.endswith("_results.csv"):
+                    csv_text = open(os.path.join(folder, f)).read()
     ev, kwargs = built[0]
+    result["csv_text"], result["returned"] = csv_text, [float(v) for v in ev.returned]
     result.update({
         "evaluators_built": len(built), "keywords": sorted(kwargs), "score_function_names": ev.score_function_names,
         "score_function_modules": {n: f.__module__ for n, f in ev.score_functions.items()},

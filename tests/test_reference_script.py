@@ -39,6 +39,39 @@ def test_reference_script_runs_unmodified_up_to_the_device_boundary():
     assert r["stopped_at"] == ["QstError", "InformationRetrievalEvaluator needs a CUDA device (no CPU fallback)"]
 
 
+@pytest.mark.skipif(not os.path.isfile("/root/reference/ir_evauation_script.py"),
+                    reason="the reference is only mounted in the authoring container")
+def test_reference_script_runs_to_completion_with_the_oracle_evaluator():
+    """The same unmodified script with the CPU ORACLE standing in for sentence-transformers' evaluator and
+    score functions (and the reference's own ``euclidean_score`` called for real): it runs to the end, i.e. the
+    restatement has the constructor, call protocol and CSV layout the script needs from ST 2.2.2 -- baseline and
+    model evaluated into one CSV (header + two rows of 2 + 3 * 68 cells), the returned value = the best
+    score function's MAP@900, and with a 169-document corpus every relevant document is inside the top 900."""
+    run = subprocess.run([sys.executable, os.path.join(HERE, "run_reference_script.py"), "--oracle"],
+                         capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in run.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert run.returncode == 0 and len(lines) == 1, (run.returncode, run.stdout[-2000:], run.stderr[-2000:])
+    r = json.loads(lines[0][len("RESULT "):])
+    assert r["bound_evaluator"] == "oracle.ir_oracle" and r["stopped_at"] is None
+    assert r["files_written"] == ["Information-Retrieval_evaluation_trained_exp5_results.csv", "command_line_args.json",
+                                  "created_eval_queries.json"]
+    rows = [ln.split(",") for ln in r["csv_text"].strip().splitlines()]
+    assert len(rows) == 3 and [len(x) for x in rows] == [206, 206, 206]
+    header = rows[0]
+    assert header[:3] == ["epoch", "steps", "cos_sim-Accuracy@1"] and header[-1] == "euclid_score-MAP@900"
+    assert len(r["returned"]) == 2
+    for row, returned in zip(rows[1:], r["returned"]):
+        cell = dict(zip(header, row))
+        assert cell["epoch"] == "-1" and cell["steps"] == "-1"
+        for fn in ("cos_sim", "dot_score", "euclid_score"):
+            assert float(cell[f"{fn}-Recall@900"]) == 1.0 and float(cell[f"{fn}-Accuracy@900"]) == 1.0
+            assert 0.0 < float(cell[f"{fn}-MAP@900"]) <= 1.0
+            recalls = [float(cell[f"{fn}-Recall@{k}"]) for k in (1, 3, 5, 10, 20, 30, 40, 50, 100, 200, 500, 900)]
+            assert recalls == sorted(recalls)                               # recall is monotone in k
+        assert returned == max(float(cell[f"{fn}-MAP@900"]) for fn in ("cos_sim", "dot_score", "euclid_score"))
+        assert 0.3 < returned < 1.0                                         # the stand-in embeddings are not trivial
+
+
 def test_known_foreign_score_callables_select_the_fused_path():
     """sentence-transformers' ``util.cos_sim`` / ``util.dot_score`` and the reference's
     ``models.evaluators.euclidean_score`` are recognised by module and name (the unmodified reference hands
