@@ -204,3 +204,49 @@ def test_fixture_is_what_the_reference_produces_now():
         assert torch.equal(ns["euclidean_score"](a, b), ir_oracle.euclidean_score(a, b))
     assert torch.equal(ns["euclidean_score"](a[0], b), ir_oracle.euclidean_score(a[0], b))
     assert torch.equal(ns["euclidean_score"](a.tolist(), b.tolist()), ir_oracle.euclidean_score(a.tolist(), b.tolist()))
+
+
+@pytest.mark.skipif(not rs.available(), reason="the reference is only mounted in the authoring container")
+def test_reference_loss_model_wrapper_drives_the_drop_in_loss_up_to_the_device_boundary():
+    """The loss protocol of SURVEY 8b from the caller's side: the reference's own
+    ``QuadrupletSentenceTransformerLossModel`` (models/quadruplet_sentence_transformer.py:9-78) takes the drop-in
+    ``GammaQuadrupletLoss`` as its ``quadruplet_loss`` (an ``nn.Module``, registered as a sub-module), runs the
+    sentence model on the four texts and calls it with the reference's keywords -- and on a box without a GPU
+    the drop-in answers with its no-CPU-fallback error instead of computing on the host.  A per-batch
+    ``additional_loss_kwargs`` entry (``reduction``) reaches ``forward`` like it reaches the reference's."""
+    import qst_b200
+    wrapper_cls = rs.load_loss_model()
+    n, table = gen.full_stack_table()
+    model = rs.TableSentenceModel(table)
+    loss = qst_b200.GammaQuadrupletLoss(gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5)
+    wrapper = wrapper_cls(st_model=model, quadruplet_loss=loss)
+    assert dict(wrapper.named_modules())["_quadruplet_loss"] is loss and loss.gamma == 0.6
+    features = [torch.arange(0, 8), torch.arange(n, n + 8), torch.arange(2 * n, 2 * n + 8), torch.arange(3 * n, 3 * n + 8)]
+    seen = {}
+    real_forward = loss.forward
+
+    def spy(*args, **kwargs):
+        seen["args"], seen["kwargs"] = args, dict(kwargs)
+        return real_forward(*args, **kwargs)
+
+    loss.forward = spy
+    with pytest.raises(qst_b200.QstError):
+        wrapper(features, None)
+    assert seen["args"] == () and sorted(seen["kwargs"]) == ["x_anchor", "x_neg", "x_part", "x_pos"]
+    assert torch.equal(seen["kwargs"]["x_pos"], table[n:n + 8])
+    # dict-shaped features + an additional loss kwarg taken from the batch (:60-66)
+    wrapper = wrapper_cls(st_model=model, quadruplet_loss=loss, additional_loss_kwargs=["reduction"])
+    batch = {"reference": features[0], "positive": features[1], "part_positive": features[2], "negative": features[3],
+             "reduction": "sum"}
+    with pytest.raises(qst_b200.QstError):
+        wrapper(batch, None)
+    assert seen["kwargs"]["reduction"] == "sum" and torch.equal(seen["kwargs"]["x_part"], table[2 * n:2 * n + 8])
+    # the same wrapper around the reference's loss computes; the drop-in must be interchangeable in that slot
+    from oracle import loss_oracle
+    ref_loss = loss_oracle.load_reference_losses().GammaQuadrupletLoss(gamma=0.6, margin_pos_neg=1.0,
+                                                                       margin_pos_part=0.5, margin_part_neg=0.5)
+    value = wrapper_cls(st_model=model, quadruplet_loss=ref_loss, additional_loss_kwargs=["reduction"])(batch, None)
+    want = loss_oracle.gamma_quadruplet_loss(table[:8], table[n:n + 8], table[2 * n:2 * n + 8], table[3 * n:3 * n + 8],
+                                             gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5,
+                                             reduction="sum")
+    assert torch.equal(value, want)
