@@ -250,3 +250,25 @@ def test_reference_loss_model_wrapper_drives_the_drop_in_loss_up_to_the_device_b
                                              gamma=0.6, margin_pos_neg=1.0, margin_pos_part=0.5, margin_part_neg=0.5,
                                              reduction="sum")
     assert torch.equal(value, want)
+
+
+@pytest.mark.skipif(not rs.available(), reason="the reference is only mounted in the authoring container")
+def test_text_order_of_a_dataset_instance_is_the_reference_to_input_example_order():
+    """models/quadruplet_sentence_transformer.py:83-97 lays a dict instance out as [reference, positive,
+    part_positive, negative]; the drop-in QuadrupletLossEvaluator reads dict instances, InputExamples and
+    (instance, label) pairs in that order."""
+    import ast
+
+    from qst_b200.loss_evaluator import QUADRUPLET_KEYS, _texts_of
+    tree = ast.parse(open(rs.LOSS_MODEL).read())
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("to_input_example", "select_single_example")]
+    ns = {"torch": torch, "random": random, "InputExample": rs.InputExample}
+    ns.update({k: getattr(__import__("typing"), k) for k in ("Tuple", "Any", "Optional", "List", "Dict", "Union")})
+    ns.update({k: v for k, v in rs._constants().items() if k.isupper()})
+    for node in wanted:
+        exec(compile(ast.Module(body=[node], type_ignores=[]), rs.LOSS_MODEL, "exec"), ns)
+    instance = {"reference": "r", "positive": "p", "part_positive": "pp", "negative": "n"}
+    example = ns["to_input_example"](dict(instance))
+    assert example.texts == ["r", "p", "pp", "n"] == [instance[k] for k in QUADRUPLET_KEYS]
+    assert _texts_of(instance) == example.texts and _texts_of(example) == example.texts
+    assert _texts_of((example, torch.tensor(0))) == example.texts and _texts_of((instance, 0)) == example.texts
